@@ -1,0 +1,81 @@
+// Context management and error reporting for libb200vqa.
+#include <string.h>
+#include <string>
+#include "context.h"
+
+namespace b200vqa {
+
+thread_local int64_t* g_launch_counter = nullptr;
+static thread_local char g_last_error[512] = "";
+
+void set_last_error(const char* what, cudaError_t e) {
+  snprintf(g_last_error, sizeof g_last_error, "%s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
+}
+
+int DeviceBuffer::reserve(size_t n) {
+  if (n <= bytes) return B200VQA_OK;
+  if (ptr) { cudaFree(ptr); ptr = nullptr; bytes = 0; }
+  size_t want = n + n / 8 + 256;
+  cudaError_t e = cudaMalloc(&ptr, want);
+  if (e != cudaSuccess) { set_last_error("workspace cudaMalloc", e); ptr = nullptr; return B200VQA_ENOMEM; }
+  bytes = want;
+  return B200VQA_OK;
+}
+void DeviceBuffer::release() { if (ptr) cudaFree(ptr); ptr = nullptr; bytes = 0; }
+
+}  // namespace b200vqa
+
+using namespace b200vqa;
+
+extern "C" int b200vqa_version(void) { return 100; }
+
+extern "C" const char* b200vqa_error_string(int code) {
+  switch (code) {
+    case B200VQA_OK: return "ok";
+    case B200VQA_EINVAL: return "invalid argument";
+    case B200VQA_ECUDA: return "CUDA error";
+    case B200VQA_ENOTLOADED: return "weights not loaded";
+    case B200VQA_ENOMEM: return "out of device memory";
+    default: return "unknown error";
+  }
+}
+
+extern "C" const char* b200vqa_last_error(void) { return g_last_error; }
+
+extern "C" int b200vqa_create(int device, b200vqa_t** out) {
+  if (!out) return B200VQA_EINVAL;
+  int count = 0;
+  VQA_CUDA(cudaGetDeviceCount(&count));
+  if (device < 0 || device >= count) return B200VQA_EINVAL;
+  VQA_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  VQA_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    snprintf(g_last_error, sizeof g_last_error, "device %d is sm_%d%d; libb200vqa is built for sm_100a only", device, prop.major, prop.minor);
+    return B200VQA_ECUDA;
+  }
+  b200vqa_ctx* h = new b200vqa_ctx();
+  h->device = device;
+  h->sm_count = prop.multiProcessorCount;
+  *out = h;
+  return B200VQA_OK;
+}
+
+extern "C" int b200vqa_destroy(b200vqa_t* h) {
+  if (!h) return B200VQA_EINVAL;
+  cudaSetDevice(h->device);
+  cudaDeviceSynchronize();
+  for (auto& kv : h->resize_tables) { cudaFree(kv.second.d_bounds); cudaFree(kv.second.d_kk); }
+  h->ws_resize.release(); h->ws_flow.release(); h->ws_resnet.release(); h->ws_vit.release(); h->ws_head.release(); h->ws_misc.release();
+  free_resnet(h->resnet); free_vit(h->vit); free_head(h->head);
+  delete h;
+  return B200VQA_OK;
+}
+
+extern "C" int64_t b200vqa_launch_count(b200vqa_t* h) { return h ? h->launches : -1; }
+
+extern "C" int b200vqa_set_gemm_impl(b200vqa_t* h, int impl) {
+  if (!h || (impl != 0 && impl != 1)) return B200VQA_EINVAL;
+  h->gemm_impl = impl;
+  return B200VQA_OK;
+}

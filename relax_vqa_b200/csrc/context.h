@@ -1,0 +1,51 @@
+// The opaque b200vqa_ctx: device, weights, resize tables, grow-only workspaces.
+#pragma once
+#include <map>
+#include <memory>
+#include <string>
+#include <utility>
+#include <vector>
+#include "common.cuh"
+
+namespace b200vqa {
+
+struct ResizeTable {          // Pillow coefficients for one (in_size -> 224, filter)
+  int ksize = 0;
+  int* d_bounds = nullptr;    // [224][2] (xmin, count)
+  int* d_kk = nullptr;        // [224][ksize] 22-bit fixed point
+};
+
+struct DeviceBuffer {         // grow-only scratch
+  void* ptr = nullptr;
+  size_t bytes = 0;
+  int reserve(size_t n);
+  void release();
+};
+
+struct ResNetWeights;         // nn_resnet.cu
+struct ViTWeights;            // nn_vit.cu
+struct HeadWeights;           // nn_head.cu
+
+}  // namespace b200vqa
+
+struct b200vqa_ctx {
+  int device = 0;
+  int sm_count = 148;
+  int gemm_impl = 0;                       // 0 tcgen05, 1 SIMT check kernels
+  int64_t launches = 0;
+  std::map<std::pair<int, int>, b200vqa::ResizeTable> resize_tables;   // (in_size, filter)
+  b200vqa::DeviceBuffer ws_resize, ws_flow, ws_resnet, ws_vit, ws_head, ws_misc;
+  b200vqa::ResNetWeights* resnet = nullptr;
+  b200vqa::ViTWeights* vit = nullptr;
+  b200vqa::HeadWeights* head = nullptr;
+};
+
+namespace b200vqa {
+struct CtxScope {             // routes launch counting to the context for the current call
+  explicit CtxScope(b200vqa_ctx* h) { g_launch_counter = h ? &h->launches : nullptr; }
+  ~CtxScope() { g_launch_counter = nullptr; }
+};
+void free_resnet(ResNetWeights*);
+void free_vit(ViTWeights*);
+void free_head(HeadWeights*);
+}  // namespace b200vqa

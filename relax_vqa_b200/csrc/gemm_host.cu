@@ -1,0 +1,96 @@
+// Host side of the tcgen05 GEMM: TMA descriptor construction (driver entry point resolved at
+// run time, so the library has no link-time dependency on libcuda), launch, and the SIMT
+// check kernels used to validate the tensor-core path on the device.
+#include <mutex>
+#include "context.h"
+#include "gemm_tcgen05.cuh"
+#include "gemm_ref.cuh"
+
+namespace b200vqa {
+
+PFN_encodeTiled get_encode_tiled() {
+  static PFN_encodeTiled fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(p);
+  });
+  return fn;
+}
+
+int make_tmap_f16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                  const uint32_t* box, const uint32_t* elem_strides) {
+  PFN_encodeTiled enc = get_encode_tiled();
+  if (!enc) { set_last_error("cuTensorMapEncodeTiled entry point", cudaErrorNotSupported); return B200VQA_ECUDA; }
+  cuuint64_t d[5], s[5];
+  cuuint32_t b[5], e[5];
+  for (int i = 0; i < rank; ++i) { d[i] = dims[i]; b[i] = box[i]; e[i] = elem_strides ? elem_strides[i] : 1; }
+  for (int i = 0; i + 1 < rank; ++i) s[i] = strides_bytes[i];
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base), d, s, b, e,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char msg[160];
+    snprintf(msg, sizeof msg, "cuTensorMapEncodeTiled rank %d failed with CUresult %d", rank, (int)r);
+    set_last_error(msg, cudaErrorInvalidValue);
+    return B200VQA_ECUDA;
+  }
+  return B200VQA_OK;
+}
+
+int launch_gemm(const CUtensorMap& map_a, const CUtensorMap& map_b, const GemmParams& p, int sm_count, cudaStream_t st) {
+  if (p.block_n % 16 || p.block_n < 16 || p.block_n > 256 || p.stages < 2 || p.stages > GEMM_MAX_STAGES) return B200VQA_EINVAL;
+  const size_t smem = gemm_smem_bytes(p.block_n, p.stages);
+  if (smem > 227 * 1024) return B200VQA_EINVAL;
+  static bool attr_set = false;
+  if (!attr_set) {
+    VQA_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  const int tiles = p.m_tiles * p.n_tiles;
+  const int grid = tiles < sm_count ? tiles : sm_count;
+  gemm_tcgen05_kernel<<<grid, GEMM_THREADS, smem, st>>>(map_a, map_b, p);
+  VQA_LAUNCH_CHECK();
+  return B200VQA_OK;
+}
+
+int pick_stages(int block_n) {
+  const size_t per = GEMM_BM * GEMM_BK * 2 + (size_t)block_n * GEMM_BK * 2;
+  int s = (int)((220 * 1024) / per);
+  if (s > 6) s = 6;
+  return s;
+}
+
+}  // namespace b200vqa
+
+using namespace b200vqa;
+
+// Plain GEMM entry (tests / profiling): D[M][N] = A[M][K] B[N][K]^T + bias
+extern "C" int b200vqa_gemm_f16(b200vqa_t* h, const void* A, const void* B, const float* bias, float* D, int M, int N,
+                                int K, int impl, void* stream) {
+  if (!h || !A || !B || !D || M <= 0 || N <= 0 || K <= 0 || K % 8) return B200VQA_EINVAL;
+  CtxScope scope(h);
+  cudaStream_t st = as_stream(stream);
+  if (impl == 1) {
+    dim3 grid(cdiv(N, 16), cdiv(M, 16)), block(16, 16);
+    ref_gemm_rowmajor<<<grid, block, 0, st>>>(static_cast<const __half*>(A), static_cast<const __half*>(B), bias, nullptr, D,
+                                               M, N, K, N, ACT_NONE, 1);
+    VQA_LAUNCH_CHECK();
+    return B200VQA_OK;
+  }
+  const int bn = N >= 256 ? 256 : ((N + 15) / 16) * 16;
+  CUtensorMap ma, mb;
+  uint64_t da[2] = {(uint64_t)K, (uint64_t)M}, db[2] = {(uint64_t)K, (uint64_t)N}, sa[1] = {(uint64_t)K * 2};
+  uint32_t boxa[2] = {GEMM_BK, GEMM_BM}, boxb[2] = {GEMM_BK, (uint32_t)bn};
+  int rc;
+  if ((rc = make_tmap_f16(&ma, A, 2, da, sa, boxa, nullptr))) return rc;
+  if ((rc = make_tmap_f16(&mb, B, 2, db, sa, boxb, nullptr))) return rc;
+  GemmParams p{};
+  p.m_tiles = cdiv(M, GEMM_BM); p.n_tiles = cdiv(N, bn); p.block_n = bn;
+  p.k_blocks_per_tap = cdiv(K, GEMM_BK); p.taps_r = p.taps_s = 1; p.stages = pick_stages(bn);
+  p.epi = EPI_ROW; p.act = ACT_NONE; p.M = M; p.N = N; p.ldo = N; p.out_is_f32 = 1; p.bias = bias; p.out = D;
+  return launch_gemm(ma, mb, p, h->sm_count, st);
+}

@@ -1,0 +1,377 @@
+// Persistent, warp-specialised tcgen05 GEMM / implicit-GEMM convolution for sm_100a.
+//
+//   D[128 x BN] (fp32, TMEM) += A[128 x 64] (fp16, smem, K-major, SW128) * B[BN x 64]^T
+//
+// Roles (256 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane),
+// warp 2 = TMEM allocator, warps 4-7 = epilogue (TMEM -> registers -> global).
+// Three pipelines: smem full/empty ring (TMA <-> MMA), TMEM full/empty double buffer
+// (MMA <-> epilogue), static round-robin tile scheduler (tile = blockIdx.x + i*gridDim.x).
+//
+// Operand A is always a 2-D K-major matrix [rowsA][K_total].  Operand B is either a 2-D
+// K-major matrix (linear layers) or an NHWC activation tensor addressed through a 4-D TMA
+// box (C, W, H, N): for a convolution tap (r, s) the box is fetched at (c0, x0*stride+s-pad,
+// y0*stride+r-pad, n0); out-of-bounds elements are zero-filled by TMA, which implements the
+// padding, and `elementStrides` implements stride 2.  The K loop runs over taps x (Cin/64).
+//
+// Epilogues:
+//   EPI_ROW  (linear layers; A rows = tokens, B rows = output features):
+//       out[m][n] = act(acc + bias[n]) (+ residual[m][n]), fp16 or fp32 row-major
+//   EPI_CONV (convolutions; A rows = output channels, B rows = output pixels):
+//       v = acc*scale[c] + shift[c] (+ identity[pix][c]); ReLU; out[pix][c] fp16 NHWC;
+//       optional per-(image, tile, channel) partial sums of v (or of the raw acc) for the
+//       fused layer-stack global average pooling - written, not atomically added, so the
+//       reduction order is fixed and results are bit-reproducible.
+#pragma once
+#include <cuda.h>
+#include "common.cuh"
+
+namespace b200vqa {
+
+constexpr int GEMM_BM = 128;
+constexpr int GEMM_BK = 64;
+constexpr int GEMM_THREADS = 256;
+constexpr int GEMM_MAX_STAGES = 8;
+constexpr uint32_t GEMM_TMEM_COLS = 512;      // two accumulator stages of up to 256 columns
+
+enum { EPI_ROW = 0, EPI_CONV = 1 };
+enum { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU = 2 };
+
+struct GemmParams {
+  // tiling
+  int m_tiles, n_tiles;          // tiles along A rows / B rows
+  int block_n;                   // B rows per tile (multiple of 16, <= 256)
+  int k_blocks_per_tap;          // Cin / 64 (or K / 64 for plain GEMM)
+  int taps_r, taps_s;            // 1x1 or 3x3
+  int stages;
+  // B addressing
+  int b_is_conv;                 // 0: 2-D [rows][K]; 1: 4-D NHWC box
+  int conv_stride, conv_pad;
+  int tw, th, tn;                // output-pixel box of one tile (block_n == tw*th*tn)
+  int tiles_y;                   // tiles per image along y (ceil(Hout/th)); x is never split
+  int Hout, Wout, Nimg;
+  // epilogue
+  int epi;                       // EPI_ROW / EPI_CONV
+  int act;
+  int M, N;                      // EPI_ROW: valid rows of A / B.  EPI_CONV: M = Cout
+  int ldo;                       // EPI_ROW: output leading dimension (elements)
+  int out_is_f32;                // EPI_ROW
+  const float* bias;             // EPI_ROW: [N] or null
+  const float* residual;         // EPI_ROW: fp32 [M][ldo] or null (may alias out)
+  void* out;
+  const float* scale;            // EPI_CONV: [Cout]
+  const float* shift;            // EPI_CONV: [Cout]
+  const __half* identity;        // EPI_CONV: NHWC fp16 [Nimg][Hout][Wout][Cout] or null
+  float* gap_partial;            // EPI_CONV: [Nimg][tiles_y][Cout] or null
+  int gap_raw;                   // pool the raw accumulator (conv1 hook is pre-BN)
+};
+
+// ------------------------------------------------------------------------------ PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug traps (sticky launch failure) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > (1u << 26)) { printf("b200vqa gemm: mbarrier timeout block %d thread %d\n", blockIdx.x, threadIdx.x); __trap(); }
+  }
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tcgen05_mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, 128-byte-swizzled operand tile: 8-row groups are 1024 B apart (SBO), LBO unused (1).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);        // start address, bits [0,14)
+  d |= (uint64_t)1 << 16;                             // leading byte offset (ignored for SW128 K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;                   // stride byte offset, bits [32,46)
+  d |= (uint64_t)1 << 46;                             // descriptor version 1 (Blackwell)
+  d |= (uint64_t)2 << 61;                             // SWIZZLE_128B
+  return d;
+}
+// kind::f16 instruction descriptor: fp16 A/B (K-major), fp32 accumulate, M = 128, N = n.
+__device__ __forceinline__ uint32_t make_idesc(int n) {
+  return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(GEMM_BM >> 4) << 24);
+}
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+
+// ------------------------------------------------------------------------------ the kernel
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                    const GemmParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t a_bytes = GEMM_BM * GEMM_BK * 2;
+  const uint32_t b_bytes = (uint32_t)p.block_n * GEMM_BK * 2;
+  const uint32_t stage_bytes = a_bytes + b_bytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
+  uint64_t* empty_bar = full_bar + GEMM_MAX_STAGES;
+  uint64_t* tmem_full = empty_bar + GEMM_MAX_STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_tiles = p.m_tiles * p.n_tiles;
+  const int k_blocks = p.taps_r * p.taps_s * p.k_blocks_per_tap;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < p.stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(GEMM_TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int mt = tile % p.m_tiles, nt = tile / p.m_tiles;
+        int bx = 0, by = 0, bn = 0;
+        if (p.b_is_conv) {
+          const int ty = nt % p.tiles_y, tg = nt / p.tiles_y;
+          by = ty * p.th * p.conv_stride - p.conv_pad;
+          bx = -p.conv_pad;
+          bn = tg * p.tn;
+        }
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + (size_t)stage * stage_bytes;
+          uint8_t* sb = sa + a_bytes;
+          mbar_expect_tx(&full_bar[stage], stage_bytes);
+          tma_load_2d(&map_a, &full_bar[stage], sa, kb * GEMM_BK, mt * GEMM_BM);
+          if (p.b_is_conv) {
+            const int tap = kb / p.k_blocks_per_tap, cb = kb % p.k_blocks_per_tap;
+            const int r = tap / p.taps_s, s = tap % p.taps_s;
+            tma_load_4d(&map_b, &full_bar[stage], sb, cb * GEMM_BK, bx + s, by + r, bn);
+          } else {
+            tma_load_2d(&map_b, &full_bar[stage], sb, kb * GEMM_BK, nt * p.block_n);
+          }
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ==================================
+    const uint32_t idesc = make_idesc(p.block_n);
+    int stage = 0; uint32_t phase = 0;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      if (lane == 0) mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+      __syncwarp();
+      tcgen05_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)acc * 256u;
+      for (int kb = 0; kb < k_blocks; ++kb) {
+        if (lane == 0) {
+          mbar_wait(&full_bar[stage], phase);
+          tcgen05_fence_after();
+          const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+          const uint64_t adesc = make_smem_desc(sa), bdesc = make_smem_desc(sa + a_bytes);
+#pragma unroll
+          for (int k = 0; k < GEMM_BK / 16; ++k)      // +32 B per K=16 step inside the swizzled row
+            tcgen05_mma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+          tcgen05_commit(&empty_bar[stage]);          // frees the smem slot when the MMAs retire
+          if (kb == k_blocks - 1) tcgen05_commit(&tmem_full[acc]);
+        }
+        __syncwarp();
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  } else if (warp >= 4) {
+    // ================================ epilogue ====================================
+    const int q = warp & 3;                           // TMEM lane quadrant of this warp
+    const int row = q * 32 + lane;                    // accumulator row owned by this thread
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int mt = tile % p.m_tiles, nt = tile / p.m_tiles;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tcgen05_fence_after();
+      const uint32_t taddr = tmem_base + (uint32_t)acc * 256u + ((uint32_t)(q * 32) << 16);
+      if (p.epi == EPI_ROW) {
+        const int m = mt * GEMM_BM + row;
+        const int n0 = nt * p.block_n;
+        for (int c0 = 0; c0 < p.block_n; c0 += 16) {
+          uint32_t v[16];
+          tmem_ld16(taddr + c0, v);
+          tmem_ld_wait();
+          if (m < p.M) {
+            const int n = n0 + c0;
+            float f[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
+            if (n + 16 <= p.N) {
+              if (p.bias) {
+#pragma unroll
+                for (int j = 0; j < 16; j += 4) {
+                  float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n + j));
+                  f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
+                }
+              }
+              if (p.act == ACT_GELU) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) f[j] = gelu_erf(f[j]);
+              } else if (p.act == ACT_RELU) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
+              }
+              const size_t o = (size_t)m * p.ldo + n;
+              if (p.residual) {
+#pragma unroll
+                for (int j = 0; j < 16; j += 4) {
+                  float4 r4 = *reinterpret_cast<const float4*>(p.residual + o + j);
+                  f[j] += r4.x; f[j + 1] += r4.y; f[j + 2] += r4.z; f[j + 3] += r4.w;
+                }
+              }
+              if (p.out_is_f32) {
+                float4* op = reinterpret_cast<float4*>(static_cast<float*>(p.out) + o);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) op[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+              } else {
+                uint32_t h[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  __half2 t = __floats2half2_rn(f[2 * j], f[2 * j + 1]);
+                  h[j] = *reinterpret_cast<uint32_t*>(&t);
+                }
+                uint4* op = reinterpret_cast<uint4*>(static_cast<__half*>(p.out) + o);
+                op[0] = make_uint4(h[0], h[1], h[2], h[3]);
+                op[1] = make_uint4(h[4], h[5], h[6], h[7]);
+              }
+            } else {                                   // ragged N tail: scalar path
+              for (int j = 0; j < 16 && n + j < p.N; ++j) {
+                float x = f[j] + (p.bias ? p.bias[n + j] : 0.f);
+                if (p.act == ACT_GELU) x = gelu_erf(x); else if (p.act == ACT_RELU) x = fmaxf(x, 0.f);
+                const size_t o = (size_t)m * p.ldo + n + j;
+                if (p.residual) x += p.residual[o];
+                if (p.out_is_f32) static_cast<float*>(p.out)[o] = x; else static_cast<__half*>(p.out)[o] = __float2half_rn(x);
+              }
+            }
+          }
+        }
+      } else {
+        // EPI_CONV: this thread owns output channel c; columns are output pixels of the box
+        const int c = mt * GEMM_BM + row;
+        const bool c_ok = c < p.M;
+        const float sc = c_ok ? p.scale[c] : 0.f, sh = c_ok ? p.shift[c] : 0.f;
+        const int ty = nt % p.tiles_y, tg = nt / p.tiles_y;
+        __half* out = static_cast<__half*>(p.out);
+        float gsum = 0.f;
+        int g_img = tg * p.tn;                          // image whose pooling partial is being accumulated
+        int x = 0, yrel = 0, n = tg * p.tn;             // running output coordinates of column `pix`
+        for (int c0 = 0; c0 < p.block_n; c0 += 16) {
+          uint32_t v[16];
+          tmem_ld16(taddr + c0, v);
+          tmem_ld_wait();
+          if (c_ok) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              if (n != g_img) {                         // tile spans several images (tn > 1)
+                if (p.gap_partial && g_img < p.Nimg) p.gap_partial[((size_t)g_img * p.tiles_y + ty) * p.M + c] = gsum;
+                g_img = n; gsum = 0.f;
+              }
+              const int y = ty * p.th + yrel;
+              if (x < p.Wout && y < p.Hout && n < p.Nimg) {
+                const float raw = __uint_as_float(v[j]);
+                const size_t o = (((size_t)n * p.Hout + y) * p.Wout + x) * p.M + c;
+                float val = fmaf(raw, sc, sh);
+                if (p.identity) val += __half2float(p.identity[o]);
+                if (p.act == ACT_RELU) val = fmaxf(val, 0.f);
+                gsum += p.gap_raw ? raw : val;
+                out[o] = __float2half_rn(val);
+              }
+              if (++x == p.tw) { x = 0; if (++yrel == p.th) { yrel = 0; ++n; } }
+            }
+          }
+        }
+        if (p.gap_partial && c_ok && g_img >= 0 && g_img < p.Nimg)
+          p.gap_partial[((size_t)g_img * p.tiles_y + ty) * p.M + c] = gsum;
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(GEMM_TMEM_COLS) : "memory");
+  }
+}
+
+inline size_t gemm_smem_bytes(int block_n, int stages) {
+  return (size_t)stages * (GEMM_BM * GEMM_BK * 2 + (size_t)block_n * GEMM_BK * 2) + (2 * GEMM_MAX_STAGES + 4) * 8 + 16 + 1024;
+}
+
+// ---------------------------------------------------------------- host: TMA descriptors
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+PFN_encodeTiled get_encode_tiled();
+
+// fp16 tensor, innermost dimension contiguous; dims/strides innermost-first; strides in bytes for dims 1..rank-1
+int make_tmap_f16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                  const uint32_t* box, const uint32_t* elem_strides);
+
+int launch_gemm(const CUtensorMap& map_a, const CUtensorMap& map_b, const GemmParams& p, int sm_count, cudaStream_t st);
+
+}  // namespace b200vqa

@@ -1,0 +1,155 @@
+// A9: Pillow's 8-bit two-pass resampler (BILINEAR-antialiased and LANCZOS), bit-exact.
+// Coefficients are computed on the host exactly as Pillow's precompute_coeffs /
+// normalize_coeffs_8bpc do (double math, 22-bit fixed point) and cached per context.
+#include <math.h>
+#include <vector>
+#include "context.h"
+
+namespace b200vqa {
+
+static const int kPrecisionBits = 32 - 8 - 2;
+
+static double filt_bilinear(double x) { x = x < 0 ? -x : x; return x < 1.0 ? 1.0 - x : 0.0; }
+static double sinc_filter(double x) { if (x == 0.0) return 1.0; x *= M_PI; return sin(x) / x; }
+static double filt_lanczos(double x) { return (-3.0 <= x && x < 3.0) ? sinc_filter(x) * sinc_filter(x / 3.0) : 0.0; }
+
+static int build_table(int in_size, int out_size, int filter, ResizeTable* t) {
+  double (*fn)(double) = filter == B200VQA_FILTER_LANCZOS ? filt_lanczos : filt_bilinear;
+  const double fsup = filter == B200VQA_FILTER_LANCZOS ? 3.0 : 1.0;
+  double scale = (double)in_size / out_size, filterscale = scale;
+  if (filterscale < 1.0) filterscale = 1.0;
+  const double support = fsup * filterscale;
+  const int ksize = (int)ceil(support) * 2 + 1;
+  std::vector<int> bounds(out_size * 2), kk((size_t)out_size * ksize, 0);
+  std::vector<double> w(ksize);
+  const double ss = 1.0 / filterscale;
+  for (int xx = 0; xx < out_size; ++xx) {
+    double center = (xx + 0.5) * scale, ww = 0.0;
+    int xmin = (int)(center - support + 0.5);
+    if (xmin < 0) xmin = 0;
+    int xmax = (int)(center + support + 0.5);
+    if (xmax > in_size) xmax = in_size;
+    xmax -= xmin;
+    for (int x = 0; x < xmax; ++x) { w[x] = fn((x + xmin - center + 0.5) * ss); ww += w[x]; }
+    for (int x = 0; x < xmax; ++x) {
+      double v = ww != 0.0 ? w[x] / ww : w[x];
+      kk[(size_t)xx * ksize + x] = v < 0 ? (int)(-0.5 + v * (1 << kPrecisionBits)) : (int)(0.5 + v * (1 << kPrecisionBits));
+    }
+    bounds[xx * 2] = xmin; bounds[xx * 2 + 1] = xmax;
+  }
+  t->ksize = ksize;
+  VQA_CUDA(cudaMalloc(&t->d_bounds, bounds.size() * sizeof(int)));
+  VQA_CUDA(cudaMalloc(&t->d_kk, kk.size() * sizeof(int)));
+  VQA_CUDA(cudaMemcpy(t->d_bounds, bounds.data(), bounds.size() * sizeof(int), cudaMemcpyHostToDevice));
+  VQA_CUDA(cudaMemcpy(t->d_kk, kk.data(), kk.size() * sizeof(int), cudaMemcpyHostToDevice));
+  return B200VQA_OK;
+}
+
+__device__ __forceinline__ uint8_t clip8(int acc) {
+  int v = acc >> kPrecisionBits;
+  return (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 : v));
+}
+
+// horizontal pass: one block per input row; the row is staged in shared memory.
+__global__ void __launch_bounds__(224)
+k7_resample_h(const uint8_t* __restrict__ src, int H, int W, const int* __restrict__ bounds, const int* __restrict__ kk,
+              int ksize, uint8_t* __restrict__ dst, int swap_rb) {
+  extern __shared__ uint8_t row[];
+  const int y = blockIdx.x, b = blockIdx.y;
+  const uint8_t* s = src + ((size_t)b * H + y) * W * 3;
+  const int nbytes = W * 3;
+  if ((nbytes & 15) == 0 && (((uintptr_t)s & 15) == 0)) {
+    for (int i = threadIdx.x; i < nbytes / 16; i += blockDim.x)
+      reinterpret_cast<uint4*>(row)[i] = __ldg(reinterpret_cast<const uint4*>(s) + i);
+  } else {
+    for (int i = threadIdx.x; i < nbytes; i += blockDim.x) row[i] = s[i];
+  }
+  __syncthreads();
+  const int xx = threadIdx.x;
+  const int xmin = bounds[xx * 2], cnt = bounds[xx * 2 + 1];
+  const int* k = kk + (size_t)xx * ksize;
+  int a0 = 1 << (kPrecisionBits - 1), a1 = a0, a2 = a0;
+  for (int i = 0; i < cnt; ++i) {
+    const int c = __ldg(k + i);
+    const uint8_t* p = row + (xmin + i) * 3;
+    a0 += p[0] * c; a1 += p[1] * c; a2 += p[2] * c;
+  }
+  uint8_t* d = dst + (((size_t)b * H + y) * 224 + xx) * 3;
+  if (swap_rb) { d[0] = clip8(a2); d[1] = clip8(a1); d[2] = clip8(a0); }
+  else { d[0] = clip8(a0); d[1] = clip8(a1); d[2] = clip8(a2); }
+}
+
+// vertical pass over a [H][224][3] image: one block per output row, one thread per (x, c).
+__global__ void __launch_bounds__(672)
+k7_resample_v(const uint8_t* __restrict__ src, int H, const int* __restrict__ bounds, const int* __restrict__ kk, int ksize,
+              uint8_t* __restrict__ dst, int swap_rb) {
+  const int yy = blockIdx.x, b = blockIdx.y, t = threadIdx.x;
+  const int ymin = bounds[yy * 2], cnt = bounds[yy * 2 + 1];
+  const int* k = kk + (size_t)yy * ksize;
+  const uint8_t* s = src + ((size_t)b * H + ymin) * 672 + t;
+  int acc = 1 << (kPrecisionBits - 1);
+  for (int i = 0; i < cnt; ++i) acc += s[(size_t)i * 672] * __ldg(k + i);
+  const int x = t / 3, c = t % 3;
+  dst[((size_t)b * 224 + yy) * 672 + x * 3 + (swap_rb ? 2 - c : c)] = clip8(acc);
+}
+
+__global__ void k7_copy_swap(const uint8_t* __restrict__ src, size_t npix, uint8_t* __restrict__ dst, int swap_rb) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npix) return;
+  uint8_t a = src[i * 3], b = src[i * 3 + 1], c = src[i * 3 + 2];
+  dst[i * 3] = swap_rb ? c : a; dst[i * 3 + 1] = b; dst[i * 3 + 2] = swap_rb ? a : c;
+}
+
+static int get_table(b200vqa_ctx* h, int in_size, int filter, ResizeTable** out) {
+  auto key = std::make_pair(in_size, filter);
+  auto it = h->resize_tables.find(key);
+  if (it == h->resize_tables.end()) {
+    ResizeTable t;
+    int rc = build_table(in_size, 224, filter, &t);
+    if (rc) return rc;
+    it = h->resize_tables.emplace(key, t).first;
+  }
+  *out = &it->second;
+  return B200VQA_OK;
+}
+
+}  // namespace b200vqa
+
+using namespace b200vqa;
+
+extern "C" int b200vqa_resize_pil(b200vqa_t* h, const uint8_t* src, int B, int H, int W, int filter, int swap_rb,
+                                  uint8_t* dst, void* stream) {
+  if (!h || !src || !dst || B <= 0 || H <= 0 || W <= 0) return B200VQA_EINVAL;
+  if (filter != B200VQA_FILTER_BILINEAR && filter != B200VQA_FILTER_LANCZOS) return B200VQA_EINVAL;
+  CtxScope scope(h);
+  cudaStream_t st = as_stream(stream);
+  const bool need_h = W != 224, need_v = H != 224;
+  if (!need_h && !need_v) {
+    size_t npix = (size_t)B * 224 * 224;
+    k7_copy_swap<<<(unsigned)((npix + 255) / 256), 256, 0, st>>>(src, npix, dst, swap_rb);
+    VQA_LAUNCH_CHECK();
+    return B200VQA_OK;
+  }
+  ResizeTable *th = nullptr, *tv = nullptr;
+  int rc;
+  if (need_h && (rc = get_table(h, W, filter, &th))) return rc;
+  if (need_v && (rc = get_table(h, H, filter, &tv))) return rc;
+  const uint8_t* vsrc = src;
+  if (need_h) {
+    uint8_t* hdst = dst;
+    if (need_v) {
+      if ((rc = h->ws_resize.reserve((size_t)B * H * 672))) return rc;
+      hdst = static_cast<uint8_t*>(h->ws_resize.ptr);
+    }
+    size_t smem = (size_t)W * 3 + 16;
+    if (smem > 48 * 1024) VQA_CUDA(cudaFuncSetAttribute(k7_resample_h, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k7_resample_h<<<dim3(H, B), 224, smem, st>>>(src, H, W, th->d_bounds, th->d_kk, th->ksize, hdst, need_v ? 0 : swap_rb);
+    VQA_LAUNCH_CHECK();
+    vsrc = hdst;
+  }
+  if (need_v) {
+    k7_resample_v<<<dim3(224, B), 672, 0, st>>>(vsrc, H, tv->d_bounds, tv->d_kk, tv->ksize, dst, swap_rb);
+    VQA_LAUNCH_CHECK();
+  }
+  return B200VQA_OK;
+}

@@ -1,0 +1,119 @@
+"""Stage-level operators on CUDA tensors: thin, typed wrappers over the C ABI.
+
+Every function enqueues on torch's current stream and returns torch tensors on the same
+device.  Reference call sites are cited in include/b200vqa.h.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import check, ptr, stream_ptr
+
+PATCH, TARGET, TOP_N = 16, 224, 196
+BILINEAR, LANCZOS = 0, 1
+
+
+class Context:
+    """Owns a b200vqa_t handle (weights, TMA descriptors, workspaces) on one device."""
+
+    def __init__(self, device=0):
+        if not torch.cuda.is_available():
+            raise _lib.B200VQAError("no CUDA device: relax_vqa_b200 has no CPU fallback")
+        self.lib = _lib.load()
+        self.device = torch.device("cuda", device)
+        torch.cuda.set_device(self.device)
+        h = C.c_void_p()
+        check(self.lib.b200vqa_create(device, C.byref(h)), "b200vqa_create")
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.b200vqa_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def launches(self):
+        return int(self.lib.b200vqa_launch_count(self.h))
+
+    def set_gemm_impl(self, impl):
+        check(self.lib.b200vqa_set_gemm_impl(self.h, int(impl)), "set_gemm_impl")
+
+
+def _u8(t):
+    assert t.dtype == torch.uint8 and t.is_cuda and t.is_contiguous()
+    return t
+
+
+def absdiff_patchsum(frame, nxt, want_residual=False, want_gray=True):
+    """frame/nxt [B,H,W,3] u8 BGR -> dict(sums [B,gh,gw] int32-valued uint32 bits, residual, gray0, gray1)."""
+    lib = _lib.load()
+    B, H, W, _ = _u8(frame).shape
+    assert _u8(nxt).shape == frame.shape
+    dev = frame.device
+    sums = torch.empty((B, H // PATCH, W // PATCH), dtype=torch.int32, device=dev)
+    residual = torch.empty_like(frame) if want_residual else None
+    g0 = torch.empty((B, H, W), dtype=torch.uint8, device=dev) if want_gray else None
+    g1 = torch.empty((B, H, W), dtype=torch.uint8, device=dev) if want_gray else None
+    check(lib.b200vqa_absdiff_patchsum_u8(ptr(frame), ptr(nxt), B, H, W, ptr(residual), ptr(sums), ptr(g0), ptr(g1),
+                                          stream_ptr(dev)), "absdiff_patchsum")
+    return dict(sums=sums, residual=residual, gray0=g0, gray1=g1)
+
+
+def patchsum(img):
+    lib = _lib.load()
+    B, H, W, _ = _u8(img).shape
+    sums = torch.empty((B, H // PATCH, W // PATCH), dtype=torch.int32, device=img.device)
+    check(lib.b200vqa_patchsum_u8(ptr(img), B, H, W, ptr(sums), stream_ptr(img.device)), "patchsum")
+    return sums
+
+
+def topk_patches(sums, top_n=TOP_N):
+    """sums [B,gh,gw] -> (pos [B,top_n,2] int32 (y,x) raster order, -1 padded; count [B] int32)."""
+    lib = _lib.load()
+    B, gh, gw = sums.shape
+    pos = torch.empty((B, top_n, 2), dtype=torch.int32, device=sums.device)
+    count = torch.empty((B,), dtype=torch.int32, device=sums.device)
+    check(lib.b200vqa_topk_patches(ptr(sums), B, gh, gw, top_n, ptr(pos), ptr(count), stream_ptr(sums.device)), "topk")
+    return pos, count
+
+
+def gather_fragments(frame, nxt, pos, count, want_ori=True, want_diff=True):
+    lib = _lib.load()
+    B, H, W, _ = _u8(frame).shape
+    dev = frame.device
+    ori = torch.empty((B, TARGET, TARGET, 3), dtype=torch.uint8, device=dev) if want_ori else None
+    diff = torch.empty((B, TARGET, TARGET, 3), dtype=torch.uint8, device=dev) if want_diff else None
+    check(lib.b200vqa_gather_fragments(ptr(frame), ptr(nxt) if nxt is not None else None, B, H, W, ptr(pos), ptr(count),
+                                       pos.shape[1], ptr(ori), ptr(diff), stream_ptr(dev)), "gather_fragments")
+    return ori, diff
+
+
+def merge_fragments(a, b):
+    lib = _lib.load()
+    assert a.shape == b.shape
+    out = torch.empty_like(_u8(a))
+    check(lib.b200vqa_merge_fragments(ptr(a), ptr(_u8(b)), a.numel(), ptr(out), stream_ptr(a.device)), "merge")
+    return out
+
+
+def resize_pil(ctx, src, filt, swap_rb=False):
+    B, H, W, _ = _u8(src).shape
+    dst = torch.empty((B, TARGET, TARGET, 3), dtype=torch.uint8, device=src.device)
+    check(ctx.lib.b200vqa_resize_pil(ctx.h, ptr(src), B, H, W, int(filt), int(swap_rb), ptr(dst), stream_ptr(src.device)), "resize_pil")
+    return dst
+
+
+def gemm_f16(ctx, A, Bm, bias=None, impl=0):
+    """D = A @ Bm.T + bias; A [M,K], Bm [N,K] fp16 -> fp32 [M,N] (test / profiling entry)."""
+    M, K = A.shape
+    N = Bm.shape[0]
+    D = torch.empty((M, N), dtype=torch.float32, device=A.device)
+    check(ctx.lib.b200vqa_gemm_f16(ctx.h, ptr(A), ptr(Bm), ptr(bias), ptr(D), M, N, K, impl, stream_ptr(A.device)), "gemm_f16")
+    return D

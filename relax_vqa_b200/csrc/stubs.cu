@@ -6,9 +6,6 @@ void free_vit(ViTWeights*) {}
 void free_head(HeadWeights*) {}
 }
 extern "C" {
-int b200vqa_farneback(b200vqa_t*, const uint8_t*, const uint8_t*, int, int, int, float*, void*) { return B200VQA_ENOTLOADED; }
-int b200vqa_flow_to_rgb(const float*, int, int, int, uint8_t*, uint32_t*, float*, void*) { return B200VQA_ENOTLOADED; }
-int b200vqa_flow_fragment_merge(const float*, const float*, int, int, int, const int32_t*, const int32_t*, int, const uint8_t*, uint8_t*, uint8_t*, void*) { return B200VQA_ENOTLOADED; }
 int b200vqa_load_resnet50(b200vqa_t*, int, const char* const*, const float* const*, const int64_t*) { return B200VQA_ENOTLOADED; }
 int b200vqa_load_vitb16(b200vqa_t*, int, const char* const*, const float* const*, const int64_t*) { return B200VQA_ENOTLOADED; }
 int b200vqa_load_head(b200vqa_t*, int, const float*, const float*, const float*, const float*, const float*, const float*, const float*, const float*, const float*, const float*, const double*, const double*, const double*) { return B200VQA_ENOTLOADED; }

@@ -117,3 +117,34 @@ def gemm_f16(ctx, A, Bm, bias=None, impl=0):
     D = torch.empty((M, N), dtype=torch.float32, device=A.device)
     check(ctx.lib.b200vqa_gemm_f16(ctx.h, ptr(A), ptr(Bm), ptr(bias), ptr(D), M, N, K, impl, stream_ptr(A.device)), "gemm_f16")
     return D
+
+
+def farneback(ctx, gray0, gray1):
+    """gray0/gray1 [B,H,W] u8 -> flow [B,H,W,2] f32 (cv2.calcOpticalFlowFarneback(...,0.5,3,15,3,5,1.2,0))."""
+    B, H, W = _u8(gray0).shape
+    flow = torch.empty((B, H, W, 2), dtype=torch.float32, device=gray0.device)
+    check(ctx.lib.b200vqa_farneback(ctx.h, ptr(gray0), ptr(_u8(gray1)), B, H, W, ptr(flow), stream_ptr(gray0.device)), "farneback")
+    return flow
+
+
+def flow_to_rgb(flow, want_rgb=True, want_sums=True):
+    """flow [B,H,W,2] -> (rgb [B,H,W,3] u8 BGR or None, sums [B,gh,gw] or None, minmax [B,2])."""
+    lib = _lib.load()
+    B, H, W, _ = flow.shape
+    dev = flow.device
+    rgb = torch.empty((B, H, W, 3), dtype=torch.uint8, device=dev) if want_rgb else None
+    sums = torch.empty((B, H // PATCH, W // PATCH), dtype=torch.int32, device=dev) if want_sums else None
+    minmax = torch.empty((B, 2), dtype=torch.float32, device=dev)
+    check(lib.b200vqa_flow_to_rgb(ptr(flow), B, H, W, ptr(rgb), ptr(sums), ptr(minmax), stream_ptr(dev)), "flow_to_rgb")
+    return rgb, sums, minmax
+
+
+def flow_fragment_merge(flow, minmax, pos, count, diff_frag, want_flow_frag=False):
+    lib = _lib.load()
+    B, H, W, _ = flow.shape
+    dev = flow.device
+    flow_frag = torch.empty((B, TARGET, TARGET, 3), dtype=torch.uint8, device=dev) if want_flow_frag else None
+    merged = torch.empty((B, TARGET, TARGET, 3), dtype=torch.uint8, device=dev)
+    check(lib.b200vqa_flow_fragment_merge(ptr(flow), ptr(minmax), B, H, W, ptr(pos), ptr(count), pos.shape[1],
+                                          ptr(diff_frag), ptr(flow_frag), ptr(merged), stream_ptr(dev)), "flow_fragment_merge")
+    return flow_frag, merged

@@ -2,6 +2,7 @@
 // run time, so the library has no link-time dependency on libcuda), launch, and the SIMT
 // check kernels used to validate the tensor-core path on the device.
 #include <mutex>
+#define B200VQA_GEMM_KERNEL_TU
 #include "context.h"
 #include "gemm_tcgen05.cuh"
 #include "gemm_ref.cuh"
@@ -64,6 +65,25 @@ int pick_stages(int block_n) {
   return s;
 }
 
+int launch_ref_gemm_rowmajor(const __half* A, const __half* B, const float* bias, const float* residual, void* out, int M, int N,
+                             int K, int ldo, int act, int out_is_f32, cudaStream_t st) {
+  dim3 grid(cdiv(N, 16), cdiv(M, 16)), block(16, 16);
+  ref_gemm_rowmajor<<<grid, block, 0, st>>>(A, B, bias, residual, out, M, N, K, ldo, act, out_is_f32);
+  VQA_LAUNCH_CHECK();
+  return B200VQA_OK;
+}
+
+int launch_ref_conv_nhwc(const __half* in, const __half* w, const float* scale, const float* shift, const __half* identity,
+                         __half* out, float* gap_sum, int gap_raw, int Nimg, int Hin, int Win, int Cin, int Hout, int Wout,
+                         int Cout, int R, int S, int stride, int pad, int act, cudaStream_t st) {
+  const size_t total = (size_t)Nimg * Hout * Wout * Cout;
+  if (gap_sum) VQA_CUDA(cudaMemsetAsync(gap_sum, 0, (size_t)Nimg * Cout * sizeof(float), st));
+  ref_conv_nhwc<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(in, w, scale, shift, identity, out, gap_sum, gap_raw, Nimg, Hin, Win,
+                                                                  Cin, Hout, Wout, Cout, R, S, stride, pad, act);
+  VQA_LAUNCH_CHECK();
+  return B200VQA_OK;
+}
+
 }  // namespace b200vqa
 
 using namespace b200vqa;
@@ -75,11 +95,8 @@ extern "C" int b200vqa_gemm_f16(b200vqa_t* h, const void* A, const void* B, cons
   CtxScope scope(h);
   cudaStream_t st = as_stream(stream);
   if (impl == 1) {
-    dim3 grid(cdiv(N, 16), cdiv(M, 16)), block(16, 16);
-    ref_gemm_rowmajor<<<grid, block, 0, st>>>(static_cast<const __half*>(A), static_cast<const __half*>(B), bias, nullptr, D,
-                                               M, N, K, N, ACT_NONE, 1);
-    VQA_LAUNCH_CHECK();
-    return B200VQA_OK;
+    return launch_ref_gemm_rowmajor(static_cast<const __half*>(A), static_cast<const __half*>(B), bias, nullptr, D, M, N, K, N,
+                                    ACT_NONE, 1, st);
   }
   const int bn = N >= 256 ? 256 : ((N + 15) / 16) * 16;
   CUtensorMap ma, mb;

@@ -141,6 +141,7 @@ __device__ __forceinline__ uint32_t make_idesc(int n) {
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 
 // ------------------------------------------------------------------------------ the kernel
+#ifdef B200VQA_GEMM_KERNEL_TU      // defined by gemm_host.cu only (one definition per library)
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                     const GemmParams p) {
@@ -358,6 +359,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   }
 }
 
+#endif  // B200VQA_GEMM_KERNEL_TU
+
 inline size_t gemm_smem_bytes(int block_n, int stages) {
   return (size_t)stages * (GEMM_BM * GEMM_BK * 2 + (size_t)block_n * GEMM_BK * 2) + (2 * GEMM_MAX_STAGES + 4) * 8 + 16 + 1024;
 }
@@ -373,5 +376,13 @@ int make_tmap_f16(CUtensorMap* map, const void* base, int rank, const uint64_t* 
                   const uint32_t* box, const uint32_t* elem_strides);
 
 int launch_gemm(const CUtensorMap& map_a, const CUtensorMap& map_b, const GemmParams& p, int sm_count, cudaStream_t st);
+int pick_stages(int block_n);
+
+// SIMT check kernels (gemm_ref.cuh), launched from other translation units through these wrappers
+int launch_ref_gemm_rowmajor(const __half* A, const __half* B, const float* bias, const float* residual, void* out, int M, int N,
+                             int K, int ldo, int act, int out_is_f32, cudaStream_t st);
+int launch_ref_conv_nhwc(const __half* in, const __half* w, const float* scale, const float* shift, const __half* identity,
+                         __half* out, float* gap_sum, int gap_raw, int Nimg, int Hin, int Win, int Cin, int Hout, int Wout,
+                         int Cout, int R, int S, int stride, int pad, int act, cudaStream_t st);
 
 }  // namespace b200vqa

@@ -1,0 +1,403 @@
+// A11 + A14 + A15: DINO ViT-B/16 forward and [mean, max, std] token pooling.
+//   reference: src/extractor/visualise_vit_layer.py:81-260 (model), :447-500 (preprocess + forward),
+//              src/main_fragment_pool.py:124-132 (pooling).
+// Residual stream fp32; GEMM operands fp16 (tcgen05, fp32 accumulate); LayerNorm, softmax and
+// pooling in fp32.  Attention is a fused per-(image, head) kernel (N = 197 fits on chip).
+#include <map>
+#include <string>
+#include <vector>
+#include "context.h"
+#include "gemm_tcgen05.cuh"
+
+namespace b200vqa {
+
+constexpr int VD = 768, VT = 197, VP = 196, VH = 12, VHD = 64, VDEPTH = 12, VMLP = 3072;
+
+struct Linear { int N = 0, K = 0; __half* w = nullptr; float* b = nullptr; CUtensorMap map_b; };
+struct VitBlock { float *ln1_w, *ln1_b, *ln2_w, *ln2_b; Linear qkv, proj, fc1, fc2; };
+struct ViTWeights {
+  Linear patch;
+  float *cls = nullptr, *pos = nullptr, *norm_w = nullptr, *norm_b = nullptr;
+  VitBlock blocks[VDEPTH];
+  std::vector<void*> allocs;
+};
+
+void free_vit(ViTWeights* v) {
+  if (!v) return;
+  for (void* p : v->allocs) cudaFree(p);
+  delete v;
+}
+
+// ------------------------------------------------------------------------------- kernels
+// ToTensor (x/255, no mean/std) + 16x16 patch extraction: [B][224][224][3] u8 -> fp16 [B*196][768],
+// k = c*256 + i*16 + j (the flattening of the conv weight [768][3][16][16]).
+__global__ void __launch_bounds__(256)
+k9_patchify(const uint8_t* __restrict__ img, int is_bgr, __half* __restrict__ out) {
+  const int p = blockIdx.x, b = blockIdx.y;              // patch index 0..195
+  const int py = p / 14, px = p % 14;
+  __half* o = out + ((size_t)b * VP + p) * VD;
+  for (int k = threadIdx.x; k < VD; k += 256) {
+    const int c = k >> 8, i = (k >> 4) & 15, j = k & 15;
+    const uint8_t u = img[(((size_t)b * 224 + py * 16 + i) * 224 + px * 16 + j) * 3 + (is_bgr ? 2 - c : c)];
+    o[k] = __float2half_rn((float)u / 255.0f);
+  }
+}
+
+// tokens: x[b][0] = cls + pos[0]; x[b][1+p] = embed[b*196+p] + pos[1+p]   (fp32)
+__global__ void __launch_bounds__(256)
+k9_assemble_tokens(const float* __restrict__ embed, const float* __restrict__ cls, const float* __restrict__ pos,
+                   float* __restrict__ x) {
+  const int t = blockIdx.x, b = blockIdx.y;
+  for (int c = threadIdx.x; c < VD; c += 256) {
+    const float v = (t == 0) ? cls[c] : embed[((size_t)b * VP + t - 1) * VD + c];
+    x[((size_t)b * VT + t) * VD + c] = v + pos[(size_t)t * VD + c];
+  }
+}
+
+// LayerNorm (eps 1e-6) over 768 channels, one warp per token, fp32 in -> fp16 out
+__global__ void __launch_bounds__(256)
+k11_layernorm(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias, __half* __restrict__ out, int rows) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * VD);
+  float4 v[6];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) { v[i] = xr[lane + 32 * i]; s += v[i].x + v[i].y + v[i].z + v[i].w; }
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / VD;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+    q += a * a + b * b + c * c + d * d;
+  }
+  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float rstd = rsqrtf(q / VD + 1e-6f);
+  __half* orow = out + (size_t)row * VD;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    const int c = (lane + 32 * i) * 4;
+    const float4 ww = *reinterpret_cast<const float4*>(w + c), bb = *reinterpret_cast<const float4*>(bias + c);
+    __half2 h0 = __floats2half2_rn((v[i].x - mean) * rstd * ww.x + bb.x, (v[i].y - mean) * rstd * ww.y + bb.y);
+    __half2 h1 = __floats2half2_rn((v[i].z - mean) * rstd * ww.z + bb.z, (v[i].w - mean) * rstd * ww.w + bb.w);
+    uint2 pk = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
+    *reinterpret_cast<uint2*>(orow + c) = pk;
+  }
+}
+
+// ---- fused attention for one (image, head): S = QK^T * scale, softmax, O = PV.  fp16 operands on
+// the warp-level tensor path (197 keys fit in registers/smem), fp32 softmax.
+constexpr int AT_NP = 208, AT_LD = 72;
+constexpr int AT_SMEM = (2 * AT_NP + 4 * 16) * AT_LD * 2;
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], const void* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(smem_u32(p)));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], const void* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(smem_u32(p)));
+}
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) { __half2 h = __floats2half2_rn(a, b); return *reinterpret_cast<uint32_t*>(&h); }
+
+__global__ void __launch_bounds__(128)
+k10_attention(const __half* __restrict__ qkv, __half* __restrict__ out, float scale) {
+  extern __shared__ __align__(16) uint8_t at_smem[];
+  typedef __half (*RowPtr)[AT_LD];
+  RowPtr sK = reinterpret_cast<RowPtr>(at_smem);
+  RowPtr sV = sK + AT_NP;
+  typedef __half (*QPtr)[16][AT_LD];
+  QPtr sQ = reinterpret_cast<QPtr>(sV + AT_NP);
+  const int hh = blockIdx.x, b = blockIdx.y;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const __half* base = qkv + (size_t)b * VT * (3 * VD) + hh * VHD;
+  for (int i = tid; i < AT_NP * 8; i += 128) {
+    const int row = i >> 3, ch = i & 7;
+    uint4 kv = make_uint4(0, 0, 0, 0), vv = kv;
+    if (row < VT) {
+      kv = *reinterpret_cast<const uint4*>(base + (size_t)row * (3 * VD) + VD + ch * 8);
+      vv = *reinterpret_cast<const uint4*>(base + (size_t)row * (3 * VD) + 2 * VD + ch * 8);
+    }
+    *reinterpret_cast<uint4*>(&sK[row][ch * 8]) = kv;
+    *reinterpret_cast<uint4*>(&sV[row][ch * 8]) = vv;
+  }
+  __syncthreads();
+  const int g = lane >> 2, t4 = lane & 3;
+  for (int qb = warp; qb < AT_NP / 16; qb += 4) {
+    for (int i = lane; i < 16 * 8; i += 32) {
+      const int r = i >> 3, ch = i & 7, row = qb * 16 + r;
+      uint4 q = make_uint4(0, 0, 0, 0);
+      if (row < VT) q = *reinterpret_cast<const uint4*>(base + (size_t)row * (3 * VD) + ch * 8);
+      *reinterpret_cast<uint4*>(&sQ[warp][r][ch * 8]) = q;
+    }
+    __syncwarp();
+    uint32_t qf[4][4];
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) ldsm_x4(qf[ks], &sQ[warp][lane & 15][ks * 16 + (lane >> 4) * 8]);
+    float s[AT_NP / 8][4];
+#pragma unroll
+    for (int nt = 0; nt < AT_NP / 8; ++nt) {
+      s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+#pragma unroll
+      for (int kp = 0; kp < 2; ++kp) {
+        uint32_t kb[4];
+        ldsm_x4(kb, &sK[nt * 8 + (lane & 7)][kp * 32 + (lane >> 3) * 8]);
+        mma16816(s[nt], qf[2 * kp], kb[0], kb[1]);
+        mma16816(s[nt], qf[2 * kp + 1], kb[2], kb[3]);
+      }
+    }
+    // softmax over the 197 valid keys; this thread owns rows g (regs 0,1) and g+8 (regs 2,3)
+    float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+    for (int nt = 0; nt < AT_NP / 8; ++nt) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int col = nt * 8 + t4 * 2 + (e & 1);
+        s[nt][e] = col < VT ? s[nt][e] * scale : -INFINITY;
+      }
+      m0 = fmaxf(m0, fmaxf(s[nt][0], s[nt][1]));
+      m1 = fmaxf(m1, fmaxf(s[nt][2], s[nt][3]));
+    }
+    m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1)); m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+    m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+    float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < AT_NP / 8; ++nt) {
+      s[nt][0] = __expf(s[nt][0] - m0); s[nt][1] = __expf(s[nt][1] - m0);
+      s[nt][2] = __expf(s[nt][2] - m1); s[nt][3] = __expf(s[nt][3] - m1);
+      l0 += s[nt][0] + s[nt][1]; l1 += s[nt][2] + s[nt][3];
+    }
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    const float r0 = 1.f / l0, r1 = 1.f / l1;
+    float o[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < AT_NP / 16; ++kk) {
+      uint32_t pf[4];
+      pf[0] = pack_h2(s[2 * kk][0] * r0, s[2 * kk][1] * r0);
+      pf[1] = pack_h2(s[2 * kk][2] * r1, s[2 * kk][3] * r1);
+      pf[2] = pack_h2(s[2 * kk + 1][0] * r0, s[2 * kk + 1][1] * r0);
+      pf[3] = pack_h2(s[2 * kk + 1][2] * r1, s[2 * kk + 1][3] * r1);
+#pragma unroll
+      for (int np = 0; np < 4; ++np) {
+        uint32_t vb[4];
+        ldsm_x4_t(vb, &sV[kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8][np * 16 + (lane >> 4) * 8]);
+        mma16816(o[2 * np], pf, vb[0], vb[1]);
+        mma16816(o[2 * np + 1], pf, vb[2], vb[3]);
+      }
+    }
+    const int row0 = qb * 16 + g, row1 = row0 + 8;
+    __half* ob = out + (size_t)b * VT * VD + hh * VHD;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      const int col = nt * 8 + t4 * 2;
+      if (row0 < VT) *reinterpret_cast<uint32_t*>(ob + (size_t)row0 * VD + col) = pack_h2(o[nt][0], o[nt][1]);
+      if (row1 < VT) *reinterpret_cast<uint32_t*>(ob + (size_t)row1 * VD + col) = pack_h2(o[nt][2], o[nt][3]);
+    }
+    __syncwarp();
+  }
+}
+
+// SIMT check version of the attention (one thread per (query, head-dim) output)
+__global__ void ref_attention(const __half* __restrict__ qkv, __half* __restrict__ out, float scale) {
+  const int hh = blockIdx.x, b = blockIdx.y, q = blockIdx.z;
+  __shared__ float p[VT];
+  __shared__ float red[64];
+  const __half* base = qkv + (size_t)b * VT * (3 * VD) + hh * VHD;
+  const int t = threadIdx.x;      // 64 threads
+  for (int k = t; k < VT; k += 64) {
+    float acc = 0.f;
+    for (int d = 0; d < VHD; ++d) acc = fmaf(__half2float(base[(size_t)q * 3 * VD + d]), __half2float(base[(size_t)k * 3 * VD + VD + d]), acc);
+    p[k] = acc * scale;
+  }
+  __syncthreads();
+  float m = -INFINITY;
+  for (int k = t; k < VT; k += 64) m = fmaxf(m, p[k]);
+  red[t] = m; __syncthreads();
+  for (int o = 32; o > 0; o >>= 1) { if (t < o) red[t] = fmaxf(red[t], red[t + o]); __syncthreads(); }
+  m = red[0]; __syncthreads();
+  float l = 0.f;
+  for (int k = t; k < VT; k += 64) { p[k] = expf(p[k] - m); l += p[k]; }
+  red[t] = l; __syncthreads();
+  for (int o = 32; o > 0; o >>= 1) { if (t < o) red[t] += red[t + o]; __syncthreads(); }
+  l = red[0];
+  float acc = 0.f;
+  for (int k = 0; k < VT; ++k) acc = fmaf(p[k] / l, __half2float(base[(size_t)k * 3 * VD + 2 * VD + t]), acc);
+  out[((size_t)b * VT + q) * VD + hh * VHD + t] = __float2half_rn(acc);
+}
+
+// final LayerNorm + pooling over the 196 patch tokens: out[b] = [mean | max | std(ddof=0)] (3 x 768)
+__global__ void __launch_bounds__(768)
+k11_final_norm_pool(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias, float* __restrict__ out) {
+  __shared__ float s_mean[VP], s_rstd[VP];
+  const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const float* xb = x + ((size_t)b * VT + 1) * VD;          // skip CLS
+  for (int t = warp; t < VP; t += 24) {
+    const float* xr = xb + (size_t)t * VD;
+    float v[24], s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 24; ++i) { v[i] = xr[lane + 32 * i]; s += v[i]; }
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s / VD;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < 24; ++i) { const float d = v[i] - mean; q += d * d; }
+    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    if (lane == 0) { s_mean[t] = mean; s_rstd[t] = rsqrtf(q / VD + 1e-6f); }
+  }
+  __syncthreads();
+  const int c = tid;
+  const float wc = w[c], bc = bias[c];
+  float sum = 0.f, mx = -INFINITY;
+  for (int t = 0; t < VP; ++t) {
+    const float y = (xb[(size_t)t * VD + c] - s_mean[t]) * s_rstd[t] * wc + bc;
+    sum += y; mx = fmaxf(mx, y);
+  }
+  const float mean = sum / VP;
+  float sq = 0.f;
+  for (int t = 0; t < VP; ++t) {
+    const float y = (xb[(size_t)t * VD + c] - s_mean[t]) * s_rstd[t] * wc + bc;
+    const float d = y - mean;
+    sq += d * d;
+  }
+  float* o = out + (size_t)b * (3 * VD);
+  o[c] = mean; o[VD + c] = mx; o[2 * VD + c] = sqrtf(sq / VP);
+}
+
+// ------------------------------------------------------------------------- weight loading
+typedef std::map<std::string, std::pair<const float*, int64_t>> TensorMap;
+
+static int upload_f32(ViTWeights* vw, const TensorMap& t, const std::string& name, int64_t numel, float** dev) {
+  auto it = t.find(name);
+  if (it == t.end() || it->second.second != numel) return B200VQA_EINVAL;
+  VQA_CUDA(cudaMalloc((void**)dev, numel * sizeof(float)));
+  vw->allocs.push_back(*dev);
+  VQA_CUDA(cudaMemcpy(*dev, it->second.first, numel * sizeof(float), cudaMemcpyHostToDevice));
+  return B200VQA_OK;
+}
+
+static int load_linear(ViTWeights* vw, const TensorMap& t, const std::string& name, int N, int K, Linear* lin) {
+  auto it = t.find(name + ".weight");
+  if (it == t.end() || it->second.second != (int64_t)N * K) return B200VQA_EINVAL;
+  std::vector<__half> w((size_t)N * K);
+  for (size_t i = 0; i < w.size(); ++i) w[i] = __float2half_rn(it->second.first[i]);
+  VQA_CUDA(cudaMalloc((void**)&lin->w, w.size() * sizeof(__half)));
+  vw->allocs.push_back(lin->w);
+  VQA_CUDA(cudaMemcpy(lin->w, w.data(), w.size() * sizeof(__half), cudaMemcpyHostToDevice));
+  int rc = upload_f32(vw, t, name + ".bias", N, &lin->b);
+  if (rc) return rc;
+  lin->N = N; lin->K = K;
+  uint64_t dims[2] = {(uint64_t)K, (uint64_t)N}, strides[1] = {(uint64_t)K * 2};
+  uint32_t box[2] = {GEMM_BK, 256};
+  return make_tmap_f16(&lin->map_b, lin->w, 2, dims, strides, box, nullptr);
+}
+
+// out[M][N] = act(A[M][K] W^T + b) (+ residual)
+static int run_linear(b200vqa_ctx* h, const Linear& lin, const __half* A, int M, void* out, int out_is_f32, int act,
+                      const float* residual, cudaStream_t st) {
+  if (h->gemm_impl == 1) {
+    return launch_ref_gemm_rowmajor(A, lin.w, lin.b, residual, out, M, lin.N, lin.K, lin.N, act, out_is_f32, st);
+  }
+  CUtensorMap ma;
+  uint64_t dims[2] = {(uint64_t)lin.K, (uint64_t)M}, strides[1] = {(uint64_t)lin.K * 2};
+  uint32_t box[2] = {GEMM_BK, GEMM_BM};
+  int rc = make_tmap_f16(&ma, A, 2, dims, strides, box, nullptr);
+  if (rc) return rc;
+  GemmParams p{};
+  p.block_n = 256;
+  p.m_tiles = cdiv(M, GEMM_BM); p.n_tiles = cdiv(lin.N, 256);
+  p.k_blocks_per_tap = lin.K / GEMM_BK; p.taps_r = p.taps_s = 1;
+  p.stages = pick_stages(256);
+  p.epi = EPI_ROW; p.act = act; p.M = M; p.N = lin.N; p.ldo = lin.N; p.out_is_f32 = out_is_f32;
+  p.bias = lin.b; p.residual = residual; p.out = out;
+  return launch_gemm(ma, lin.map_b, p, h->sm_count, st);
+}
+
+}  // namespace b200vqa
+
+using namespace b200vqa;
+
+extern "C" int b200vqa_load_vitb16(b200vqa_t* h, int n, const char* const* names, const float* const* h_ptrs,
+                                   const int64_t* numels) {
+  if (!h || n <= 0 || !names || !h_ptrs || !numels) return B200VQA_EINVAL;
+  VQA_CUDA(cudaSetDevice(h->device));
+  TensorMap t;
+  for (int i = 0; i < n; ++i) t[names[i]] = std::make_pair(h_ptrs[i], numels[i]);
+  ViTWeights* vw = new ViTWeights();
+  int rc = load_linear(vw, t, "patch_embed.proj", VD, VD, &vw->patch);
+  if (!rc) rc = upload_f32(vw, t, "cls_token", VD, &vw->cls);
+  if (!rc) rc = upload_f32(vw, t, "pos_embed", (int64_t)VT * VD, &vw->pos);
+  if (!rc) rc = upload_f32(vw, t, "norm.weight", VD, &vw->norm_w);
+  if (!rc) rc = upload_f32(vw, t, "norm.bias", VD, &vw->norm_b);
+  for (int i = 0; i < VDEPTH && !rc; ++i) {
+    const std::string p = "blocks." + std::to_string(i);
+    VitBlock& bk = vw->blocks[i];
+    rc = upload_f32(vw, t, p + ".norm1.weight", VD, &bk.ln1_w);
+    if (!rc) rc = upload_f32(vw, t, p + ".norm1.bias", VD, &bk.ln1_b);
+    if (!rc) rc = upload_f32(vw, t, p + ".norm2.weight", VD, &bk.ln2_w);
+    if (!rc) rc = upload_f32(vw, t, p + ".norm2.bias", VD, &bk.ln2_b);
+    if (!rc) rc = load_linear(vw, t, p + ".attn.qkv", 3 * VD, VD, &bk.qkv);
+    if (!rc) rc = load_linear(vw, t, p + ".attn.proj", VD, VD, &bk.proj);
+    if (!rc) rc = load_linear(vw, t, p + ".mlp.fc1", VMLP, VD, &bk.fc1);
+    if (!rc) rc = load_linear(vw, t, p + ".mlp.fc2", VD, VMLP, &bk.fc2);
+  }
+  if (rc) { free_vit(vw); return rc; }
+  free_vit(h->vit);
+  h->vit = vw;
+  return B200VQA_OK;
+}
+
+extern "C" int b200vqa_vitb16_features(b200vqa_t* h, const uint8_t* img, int B, int is_bgr, float* out, void* stream) {
+  if (!h || !img || !out || B <= 0) return B200VQA_EINVAL;
+  if (!h->vit) return B200VQA_ENOTLOADED;
+  CtxScope scope(h);
+  cudaStream_t st = as_stream(stream);
+  const ViTWeights& vw = *h->vit;
+  static bool attr_done = false;
+  if (!attr_done) {
+    VQA_CUDA(cudaFuncSetAttribute(k10_attention, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
+    attr_done = true;
+  }
+  const int CH = 128;
+  const int nb = B < CH ? B : CH;
+  const size_t M = (size_t)nb * VT;
+  size_t off = 0;
+  auto carve = [&](size_t bytes) { size_t o = off; off += (bytes + 1023) / 1024 * 1024; return o; };
+  const size_t o_x = carve(M * VD * 4), o_h = carve(M * VD * 2), o_big = carve(M * VMLP * 2), o_att = carve(M * VD * 2);
+  const size_t o_emb = carve((size_t)nb * VP * VD * 4);
+  int rc = h->ws_vit.reserve(off);
+  if (rc) return rc;
+  uint8_t* ws = static_cast<uint8_t*>(h->ws_vit.ptr);
+  float* x = (float*)(ws + o_x); __half* hbuf = (__half*)(ws + o_h); __half* big = (__half*)(ws + o_big);
+  __half* att = (__half*)(ws + o_att); float* emb = (float*)(ws + o_emb);
+  for (int b0 = 0; b0 < B; b0 += nb) {
+    const int n = (B - b0) < nb ? (B - b0) : nb;
+    const int m = n * VT;
+    k9_patchify<<<dim3(VP, n), 256, 0, st>>>(img + (size_t)b0 * 224 * 224 * 3, is_bgr, hbuf);
+    VQA_LAUNCH_CHECK();
+    if ((rc = run_linear(h, vw.patch, hbuf, n * VP, emb, 1, ACT_NONE, nullptr, st))) return rc;
+    k9_assemble_tokens<<<dim3(VT, n), 256, 0, st>>>(emb, vw.cls, vw.pos, x);
+    VQA_LAUNCH_CHECK();
+    for (int l = 0; l < VDEPTH; ++l) {
+      const VitBlock& bk = vw.blocks[l];
+      k11_layernorm<<<cdiv(m, 8), 256, 0, st>>>(x, bk.ln1_w, bk.ln1_b, hbuf, m);
+      VQA_LAUNCH_CHECK();
+      if ((rc = run_linear(h, bk.qkv, hbuf, m, big, 0, ACT_NONE, nullptr, st))) return rc;
+      if (h->gemm_impl == 1) ref_attention<<<dim3(VH, n, VT), 64, 0, st>>>(big, att, 0.125f);
+      else k10_attention<<<dim3(VH, n), 128, AT_SMEM, st>>>(big, att, 0.125f);
+      VQA_LAUNCH_CHECK();
+      if ((rc = run_linear(h, bk.proj, att, m, x, 1, ACT_NONE, x, st))) return rc;
+      k11_layernorm<<<cdiv(m, 8), 256, 0, st>>>(x, bk.ln2_w, bk.ln2_b, hbuf, m);
+      VQA_LAUNCH_CHECK();
+      if ((rc = run_linear(h, bk.fc1, hbuf, m, big, 0, ACT_GELU, nullptr, st))) return rc;
+      if ((rc = run_linear(h, bk.fc2, big, m, x, 1, ACT_NONE, x, st))) return rc;
+    }
+    k11_final_norm_pool<<<n, 768, 0, st>>>(x, vw.norm_w, vw.norm_b, out + (size_t)b0 * B200VQA_VIT_POOL);
+    VQA_LAUNCH_CHECK();
+  }
+  return B200VQA_OK;
+}

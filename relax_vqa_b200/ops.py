@@ -148,3 +148,73 @@ def flow_fragment_merge(flow, minmax, pos, count, diff_frag, want_flow_frag=Fals
     check(lib.b200vqa_flow_fragment_merge(ptr(flow), ptr(minmax), B, H, W, ptr(pos), ptr(count), pos.shape[1],
                                           ptr(diff_frag), ptr(flow_frag), ptr(merged), stream_ptr(dev)), "flow_fragment_merge")
     return flow_frag, merged
+
+
+# ------------------------------------------------------------------ networks and head
+def _load_state_dict(ctx, fn, sd, what):
+    items = [(k, v.detach().to(torch.float32).contiguous().cpu()) for k, v in sd.items()
+             if torch.is_tensor(v) and v.dtype.is_floating_point]
+    n = len(items)
+    names = (C.c_char_p * n)(*[k.encode() for k, _ in items])
+    ptrs = (C.c_void_p * n)(*[v.data_ptr() for _, v in items])
+    numels = (C.c_int64 * n)(*[v.numel() for _, v in items])
+    check(fn(ctx.h, n, names, ptrs, numels), what)
+
+
+def load_resnet50(ctx, state_dict):
+    """state_dict: torchvision resnet50 keys (pretrained=True in the reference, visualise_resnet.py:21)."""
+    _load_state_dict(ctx, ctx.lib.b200vqa_load_resnet50, state_dict, "load_resnet50")
+
+
+def load_vitb16(ctx, state_dict):
+    """state_dict: DINO ViT-B/16 keys (visualise_vit_layer.py:304-330)."""
+    _load_state_dict(ctx, ctx.lib.b200vqa_load_vitb16, state_dict, "load_vitb16")
+
+
+def load_head(ctx, state_dict, imputer_mean, scaler_scale, scaler_min):
+    """Mlp state dict (possibly SWA-wrapped) + fitted imputer / scaler attributes (float64)."""
+    from .weights import fix_state_dict
+    import numpy as np
+    sd = {k: v.detach().to(torch.float32).contiguous().cpu() for k, v in fix_state_dict(state_dict).items()
+          if torch.is_tensor(v) and v.dtype.is_floating_point}
+    keep = [np.ascontiguousarray(np.asarray(a, dtype=np.float64)) for a in (imputer_mean, scaler_scale, scaler_min)]
+    p = lambda t: C.c_void_p(t.data_ptr())
+    check(ctx.lib.b200vqa_load_head(ctx.h, sd["fc1.weight"].shape[1], p(sd["fc1.weight"]), p(sd["fc1.bias"]), p(sd["bn1.weight"]),
+                                    p(sd["bn1.bias"]), p(sd["bn1.running_mean"]), p(sd["bn1.running_var"]), p(sd["fc2.weight"]),
+                                    p(sd["fc2.bias"]), p(sd["fc3.weight"]), p(sd["fc3.bias"]),
+                                    C.c_void_p(keep[0].ctypes.data), C.c_void_p(keep[1].ctypes.data), C.c_void_p(keep[2].ctypes.data)),
+          "load_head")
+
+
+def resnet50_features(ctx, img, is_bgr=True, want_stack=True, want_pool=False):
+    """img [B,224,224,3] u8 -> (stack [B,13120] | None, pool [B,2051] | None)."""
+    B = _u8(img).shape[0]
+    stack = torch.empty((B, 13120), dtype=torch.float32, device=img.device) if want_stack else None
+    pool = torch.empty((B, 2051), dtype=torch.float32, device=img.device) if want_pool else None
+    check(ctx.lib.b200vqa_resnet50_features(ctx.h, ptr(img), B, int(is_bgr), ptr(stack), ptr(pool), stream_ptr(img.device)),
+          "resnet50_features")
+    return stack, pool
+
+
+def vitb16_features(ctx, img, is_bgr=True):
+    B = _u8(img).shape[0]
+    out = torch.empty((B, 2304), dtype=torch.float32, device=img.device)
+    check(ctx.lib.b200vqa_vitb16_features(ctx.h, ptr(img), B, int(is_bgr), ptr(out), stream_ptr(img.device)), "vitb16_features")
+    return out
+
+
+def temporal_mean_concat(full_stack, full_vit, frag_stack, frag_pool, frag_vit_ori, frag_vit_mer, full_off, pair_off):
+    lib = _lib.load()
+    V = full_off.numel() - 1
+    feats = torch.empty((V, 35203), dtype=torch.float32, device=full_stack.device)
+    check(lib.b200vqa_temporal_mean_concat(ptr(full_stack), ptr(full_vit), ptr(frag_stack), ptr(frag_pool), ptr(frag_vit_ori),
+                                           ptr(frag_vit_mer), ptr(full_off), ptr(pair_off), V, ptr(feats),
+                                           stream_ptr(full_stack.device)), "temporal_mean_concat")
+    return feats
+
+
+def head_forward(ctx, features):
+    V = features.shape[0]
+    score = torch.empty((V,), dtype=torch.float32, device=features.device)
+    check(ctx.lib.b200vqa_head_forward(ctx.h, ptr(features), V, ptr(score), stream_ptr(features.device)), "head_forward")
+    return score

@@ -1,0 +1,240 @@
+#!/usr/bin/env python
+"""Benchmark of the ReLaX-VQA hot path: 1080p videos/s end to end (features + MLP).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo (N>1: launched by torchrun)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port)
+
+A step = one pass of the hot path over one batch of `--clips` synthetic LIVE-VQC-shaped clips
+(1920x1080, 300 frames @29.97 -> 22 sampled pairs) per GPU.  Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = "1080p-10s"
+H, W, PAIRS = 1080, 1920, 22
+# algorithmic figures per sampled pair
+DENSE_GFLOP_PER_PAIR = 129.9            # 3 x ResNet-50 (8.178) + 3 x ViT-B/16 (35.126)
+BW_BYTES_PER_PAIR = 335.0 * H * W       # bandwidth stages (absdiff/patch sums, Farneback, colouring, resizes)
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm_gbs=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]), src="measured")
+    return dict(hbm_gbs=6650.0, tf_burst=1590.0, tf_sustained=1400.0, src="fallback")
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            for n, v in zip(names, r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        mx = max((int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()), default=None)
+        return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=mx, reasons=sorted(reasons), samples=len(sm))
+
+
+def cpu_reference_sample(n_pairs=1, threads=None):
+    """Times the CPU restatement of the reference (oracle/) on `n_pairs` 1080p pairs + their full frames.
+    Uses cv2's Farneback (the reference's own dependency) for the flow stage.  Returns seconds per pair."""
+    import cv2
+    import torch
+    from oracle import pipeline as P
+    from relax_vqa_b200 import synth, weights
+    if threads:
+        torch.set_num_threads(threads)
+    rsd, vsd = weights.seeded_resnet50_state_dict(), weights.seeded_vitb16_state_dict()
+    fr, nx = synth.make_clip(0, H, W, n_pairs)
+    flow = lambda a, b: cv2.calcOpticalFlowFarneback(a, b, None, 0.5, 3, 15, 3, 5, 1.2, 0)
+    t0 = time.perf_counter()
+    blocks = P.video_feature_blocks(fr, nx, rsd, vsd, flow_fn=flow)
+    P.video_vector(blocks)
+    return (time.perf_counter() - t0) / n_pairs
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path (Python reference -> the oracle port,
+    one backbone forward per image instead of the reference's 15, i.e. favourable to the CPU), all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    for _ in range(min(args.warmup, 1)):
+        cpu_reference_sample(1)
+    times = [cpu_reference_sample(1) for _ in range(max(1, min(args.steps, 3)))]
+    per_pair = sum(times) / len(times)
+    vps = 1.0 / (per_pair * PAIRS)
+    line = dict(impl="reference", metric="videos_per_sec_1080p_e2e", value=vps, unit="videos/s", n_gpus=args.gpus, steps=len(times),
+                warmup=min(args.warmup, 1), ms_per_step=per_pair * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None,
+                dtype="f32", data="synthetic", config=dict(workload=WORKLOAD, width=W, height=H, pairs_per_clip=PAIRS),
+                cpu_baseline=dict(value=vps, unit="videos/s", cores=cores, kind="port",
+                                  sample="1 sampled 1080p pair (+1 full frame) per step through oracle/pipeline.py with cv2 Farneback; "
+                                         "per-clip time = 22 x per-pair time"),
+                e2e=dict(value=vps, unit="videos/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--clips", type=int, default=4, help="clips per GPU per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from relax_vqa_b200 import weights
+    from relax_vqa_b200.engine import Engine, synthetic_clips_on_device
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    warmup = max(args.warmup, 3)
+    eng = Engine(local, head_sd=weights.seeded_head_state_dict())
+    clips = synthetic_clips_on_device(args.clips, H, W, PAIRS, eng.device, seed=1000 + rank)
+    stream = torch.cuda.current_stream()
+
+    def gather(feats, score):
+        if world == 1:
+            return feats, score
+        fl = [torch.empty_like(feats) for _ in range(world)]
+        sl = [torch.empty_like(score) for _ in range(world)]
+        dist.all_gather(fl, feats)
+        dist.all_gather(sl, score)
+        return torch.cat(fl), torch.cat(sl)
+
+    def step():
+        feats, score = eng.predict(clips, "live_vqc")
+        return gather(feats, score)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = eng.ctx.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for _ in range(args.steps):
+        feats, score = step()
+    e1.record(stream)
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=eng.device)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    launches = eng.ctx.launches - l0
+    clocks = sampler.stop() if rank == 0 else None
+    videos = world * args.clips * args.steps
+    value = videos / (ms / 1e3)
+
+    # ---- e2e: same metric through the public API with HOST (pinned) buffers, H2D + D2H inside the timed region
+    host = [(c.frames.cpu().pin_memory(), c.nexts.cpu().pin_memory()) for c in clips]
+    h2d = sum(f.numel() + n.numel() for f, n in host)
+    for _ in range(2):
+        eng.predict_host(host, "live_vqc")
+    barrier()
+    e2e_steps = max(2, min(args.steps, 5))
+    t0 = torch.cuda.Event(enable_timing=True)
+    t1 = torch.cuda.Event(enable_timing=True)
+    t0.record(stream)
+    for _ in range(e2e_steps):
+        f_, s_ = eng.predict_host(host, "live_vqc")
+    t1.record(stream)
+    barrier()
+    e2e_ms = torch.tensor([t0.elapsed_time(t1)], device=eng.device)
+    if world > 1:
+        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+    e2e_value = world * args.clips * e2e_steps / (float(e2e_ms.item()) / 1e3)
+
+    # ---- roofline of the dominant kernel (tcgen05 GEMM / implicit-GEMM conv): CUDA events around every launch
+    peaks = measured_peaks()
+    eng.ctx.set_profiling(True)
+    eng.ctx.profile_read()
+    for _ in range(2):
+        eng.predict(clips, "live_vqc")
+    gemm_ms, gemm_launches, gemm_flops = eng.ctx.profile_read()
+    eng.ctx.set_profiling(False)
+    step_ms = ms / args.steps
+    achieved = gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
+    roofline = dict(bound="tensor", kernel="gemm_tcgen05_kernel", achieved=achieved, peak=peaks["tf_sustained"], unit="TFLOP/s",
+                    frac=achieved / peaks["tf_sustained"], traffic=None, peak_source=peaks["src"] + " (sustained fp16/bf16 dense)",
+                    launches_per_step=gemm_launches // 2, kernel_ms_per_step=gemm_ms / 2, share_of_step=(gemm_ms / 2) / step_ms,
+                    algorithmic_gflop_per_pair=gemm_flops / 2 / (args.clips * PAIRS) / 1e9)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        per_pair = cpu_reference_sample(1)
+        cpu = dict(value=1.0 / (per_pair * PAIRS), unit="videos/s", cores=torch.get_num_threads(), kind="port",
+                   sample=f"1 sampled 1080p pair + 1 full frame through oracle/pipeline.py (cv2 Farneback), {per_pair:.1f} s; clip = 22 pairs")
+    line = dict(metric="videos_per_sec_1080p_e2e", value=value, unit="videos/s", n_gpus=world, steps=args.steps, warmup=warmup,
+                ms_per_step=step_ms, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f16", data="synthetic",
+                config=dict(workload=WORKLOAD, width=W, height=H, pairs_per_clip=PAIRS, clips_per_gpu_per_step=args.clips,
+                            timing="inputs larger than L2 (%.0f MB per step per GPU)" % (h2d / 1e6), parallelism=f"video-sharded x{world}"),
+                clocks=clocks, gpu_launches=int(launches),
+                e2e=dict(value=e2e_value, unit="videos/s", h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(4 * args.clips)),
+                roofline=roofline, cpu_baseline=cpu)
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

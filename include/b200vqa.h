@@ -151,6 +151,11 @@ int b200vqa_gemm_f16(b200vqa_t* h, const void* A, const void* B, const float* bi
 int64_t b200vqa_launch_count(b200vqa_t* h);
 /* debug switch: 0 = tcgen05 (default), 1 = SIMT check kernels for every GEMM/conv */
 int b200vqa_set_gemm_impl(b200vqa_t* h, int impl);
+/* profiling: when on, every tcgen05 GEMM/conv launch is bracketed by CUDA events on its stream.
+ * b200vqa_profile_read synchronises, returns the summed device time (ms), the launch count and the
+ * algorithmic FLOPs (2*M*N*K of the un-padded problems) since the last read, and resets them. */
+int b200vqa_set_profiling(b200vqa_t* h, int on);
+int b200vqa_profile_read(b200vqa_t* h, double* gemm_ms, int64_t* gemm_launches, double* gemm_flops);
 
 #ifdef __cplusplus
 }

@@ -41,6 +41,8 @@ SIGNATURES = {
     "b200vqa_gemm_f16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "b200vqa_launch_count": (c_int64, [c_void_p]),
     "b200vqa_set_gemm_impl": (c_int, [c_void_p, c_int]),
+    "b200vqa_set_profiling": (c_int, [c_void_p, c_int]),
+    "b200vqa_profile_read": (c_int, [c_void_p, C.POINTER(C.c_double), C.POINTER(c_int64), C.POINTER(C.c_double)]),
 }
 
 

@@ -6,6 +6,7 @@
 namespace b200vqa {
 
 thread_local int64_t* g_launch_counter = nullptr;
+thread_local b200vqa_ctx* g_ctx = nullptr;
 static thread_local char g_last_error[512] = "";
 
 void set_last_error(const char* what, cudaError_t e) {
@@ -67,6 +68,8 @@ extern "C" int b200vqa_destroy(b200vqa_t* h) {
   cudaDeviceSynchronize();
   for (auto& kv : h->resize_tables) { cudaFree(kv.second.d_bounds); cudaFree(kv.second.d_kk); }
   h->ws_resize.release(); h->ws_flow.release(); h->ws_resnet.release(); h->ws_vit.release(); h->ws_head.release(); h->ws_misc.release();
+  for (auto& ev : h->prof_events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
+  for (auto& ev : h->prof_pool) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
   free_resnet(h->resnet); free_vit(h->vit); free_head(h->head);
   delete h;
   return B200VQA_OK;
@@ -77,5 +80,30 @@ extern "C" int64_t b200vqa_launch_count(b200vqa_t* h) { return h ? h->launches :
 extern "C" int b200vqa_set_gemm_impl(b200vqa_t* h, int impl) {
   if (!h || (impl != 0 && impl != 1)) return B200VQA_EINVAL;
   h->gemm_impl = impl;
+  return B200VQA_OK;
+}
+
+extern "C" int b200vqa_set_profiling(b200vqa_t* h, int on) {
+  if (!h) return B200VQA_EINVAL;
+  h->profiling = on ? 1 : 0;
+  return B200VQA_OK;
+}
+
+extern "C" int b200vqa_profile_read(b200vqa_t* h, double* gemm_ms, int64_t* gemm_launches, double* gemm_flops) {
+  if (!h) return B200VQA_EINVAL;
+  VQA_CUDA(cudaSetDevice(h->device));
+  VQA_CUDA(cudaDeviceSynchronize());
+  double ms = 0.0;
+  for (auto& ev : h->prof_events) {
+    float t = 0.f;
+    VQA_CUDA(cudaEventElapsedTime(&t, ev.first, ev.second));
+    ms += t;
+    h->prof_pool.push_back(ev);
+  }
+  if (gemm_ms) *gemm_ms = ms;
+  if (gemm_launches) *gemm_launches = (int64_t)h->prof_events.size();
+  if (gemm_flops) *gemm_flops = h->prof_flops;
+  h->prof_events.clear();
+  h->prof_flops = 0.0;
   return B200VQA_OK;
 }

@@ -33,6 +33,10 @@ struct b200vqa_ctx {
   int sm_count = 148;
   int gemm_impl = 0;                       // 0 tcgen05, 1 SIMT check kernels
   int64_t launches = 0;
+  int profiling = 0;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_pool;
+  double prof_flops = 0.0;
   std::map<std::pair<int, int>, b200vqa::ResizeTable> resize_tables;   // (in_size, filter)
   b200vqa::DeviceBuffer ws_resize, ws_flow, ws_resnet, ws_vit, ws_head, ws_misc;
   b200vqa::ResNetWeights* resnet = nullptr;
@@ -41,9 +45,10 @@ struct b200vqa_ctx {
 };
 
 namespace b200vqa {
+extern thread_local b200vqa_ctx* g_ctx;
 struct CtxScope {             // routes launch counting to the context for the current call
-  explicit CtxScope(b200vqa_ctx* h) { g_launch_counter = h ? &h->launches : nullptr; }
-  ~CtxScope() { g_launch_counter = nullptr; }
+  explicit CtxScope(b200vqa_ctx* h) { g_launch_counter = h ? &h->launches : nullptr; g_ctx = h; }
+  ~CtxScope() { g_launch_counter = nullptr; g_ctx = nullptr; }
 };
 void free_resnet(ResNetWeights*);
 void free_vit(ViTWeights*);

@@ -53,7 +53,23 @@ int launch_gemm(const CUtensorMap& map_a, const CUtensorMap& map_b, const GemmPa
   }
   const int tiles = p.m_tiles * p.n_tiles;
   const int grid = tiles < sm_count ? tiles : sm_count;
+  b200vqa_ctx* ctx = g_ctx;
+  std::pair<cudaEvent_t, cudaEvent_t> ev{};
+  const bool prof = ctx && ctx->profiling;
+  if (prof) {
+    if (!ctx->prof_pool.empty()) { ev = ctx->prof_pool.back(); ctx->prof_pool.pop_back(); }
+    else { VQA_CUDA(cudaEventCreate(&ev.first)); VQA_CUDA(cudaEventCreate(&ev.second)); }
+    VQA_CUDA(cudaEventRecord(ev.first, st));
+  }
   gemm_tcgen05_kernel<<<grid, GEMM_THREADS, smem, st>>>(map_a, map_b, p);
+  if (prof) {
+    VQA_CUDA(cudaEventRecord(ev.second, st));
+    ctx->prof_events.push_back(ev);
+    // algorithmic FLOPs of the un-padded problem
+    const double kdepth = (double)p.taps_r * p.taps_s * p.k_blocks_per_tap * GEMM_BK;
+    if (p.epi == EPI_ROW) ctx->prof_flops += 2.0 * p.M * p.N * kdepth;
+    else ctx->prof_flops += 2.0 * p.M * ((double)p.Nimg * p.Hout * p.Wout) * (p.b_is_conv ? kdepth : 147.0);
+  }
   VQA_LAUNCH_CHECK();
   return B200VQA_OK;
 }

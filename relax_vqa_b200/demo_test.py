@@ -1,0 +1,53 @@
+"""Drop-in for src/demo_test.py::evaluate_video_quality on pre-sampled frames.
+
+Frame sampling (ffmpeg, src/extractor/vf_extract.py) is upstream of the hot path:
+this entry point reads the PNGs the reference's sampler would have written."""
+import glob
+import os
+
+import cv2
+import numpy as np
+import torch
+from joblib import load
+
+from . import runtime
+from .engine import Clip
+from .weights import fix_state_dict   # noqa: F401  (re-exported: src/demo_test.py:25-35)
+
+
+def _sorted_frames(folder, video_name):
+    paths = [p for p in glob.glob(os.path.join(folder, f'{video_name}_*.png'))]
+    orig = sorted([p for p in paths if '_next' not in os.path.basename(p) and os.path.basename(p)[len(video_name) + 1:-4].isdigit()],
+                  key=lambda x: int(x.split('_')[-1].split('.')[0]))
+    nxt = sorted([p for p in paths if os.path.basename(p).endswith('_next.png')], key=lambda x: int(x.split('_')[-2]))
+    return orig, nxt
+
+
+def load_clip(sampled_frame_path, sampled_fragment_path, video_name, device):
+    full, _ = _sorted_frames(sampled_frame_path, video_name)
+    orig, nxt = _sorted_frames(sampled_fragment_path, video_name)
+    n = min(len(orig), len(nxt))
+    rd = lambda ps: torch.from_numpy(np.stack([cv2.imread(p) for p in ps])).to(device)
+    # the full-frame blocks average over all sampled frames, the fragment blocks over pairs (ref :80-87, :104)
+    if [os.path.basename(p) for p in full[:n]] != [os.path.basename(p) for p in orig[:n]]:
+        raise ValueError("sampled-frame and fragment folders disagree")
+    return Clip(rd(full), rd(nxt[:n]))
+
+
+def evaluate_video_quality(config):
+    """ref :51-219.  Same config keys; returns the predicted score (float)."""
+    eng = runtime.engine()
+    video_type, video_name = config['video_type'], config['video_name']
+    save_path = config['save_path']
+    base = config.get('sampled_root', "../video_sampled_frame/original_sampled_frame/")
+    clip = load_clip(os.path.join(base, "test_sampled_frames"), os.path.join(base, "test_sampled_fragment"), video_name, eng.device)
+    imputer = load(f'{save_path}/scaler/{video_type}_imputer.pkl')
+    scaler = load(f'{save_path}/scaler/{video_type}_scaler.pkl')
+    if config['is_finetune'] is True:
+        model_path = os.path.join(save_path, f"fine_tune_model/{video_type}_relaxvqa_{config['select_criteria']}_fine_tuned_model.pth")
+    else:
+        model_path = os.path.join(save_path, f"{config['train_data_name']}_relaxvqa_{config['select_criteria']}_trained_median_model_param_onLSVQ_TEST.pth")
+    state_dict = torch.load(model_path, map_location='cpu')
+    eng.load_head(state_dict, imputer.statistics_, scaler.scale_, scaler.min_)
+    _, score = eng.predict([clip], video_type, is_finetune=config['is_finetune'] is True)
+    return float(score[0].item())

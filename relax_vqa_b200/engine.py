@@ -1,0 +1,142 @@
+"""Batched fast path: sampled frame pairs -> 35,203-dim video vectors -> MOS, all on one B200.
+
+This is the call a user makes (``Engine.extract`` / ``Engine.predict``); the reference-named
+per-image functions in ``main_fragment_layerstack`` etc. are thin views over the same kernels.
+Stage order follows src/demo_test.py:76-219; every stage is a C-ABI call (include/b200vqa.h).
+"""
+from dataclasses import dataclass
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import ops, weights
+
+
+@dataclass
+class Clip:
+    """Sampled frames of one video, BGR uint8 (what cv2.imread returns for the reference's PNGs).
+
+    frames: [Tf, H, W, 3]  frames n with n % k == 0        (process_video,  vf_extract.py:103-111)
+    nexts : [Tp, H, W, 3]  frames n with (n-1) % k == 0    (process_video_residual, :113-121)
+    Pair i is (frames[i], nexts[i]); Tp <= Tf."""
+    frames: torch.Tensor
+    nexts: torch.Tensor
+
+
+class Engine:
+    def __init__(self, device=0, resnet_sd=None, vit_sd=None, head_sd=None, imputer_mean=None, scaler_scale=None,
+                 scaler_min=None, seed_if_missing=True):
+        self.ctx = ops.Context(device)
+        self.device = self.ctx.device
+        if resnet_sd is None and seed_if_missing:
+            resnet_sd = weights.seeded_resnet50_state_dict()
+        if vit_sd is None and seed_if_missing:
+            vit_sd = weights.seeded_vitb16_state_dict()
+        ops.load_resnet50(self.ctx, resnet_sd)
+        ops.load_vitb16(self.ctx, vit_sd)
+        self.has_head = False
+        if head_sd is not None:
+            self.load_head(head_sd, imputer_mean, scaler_scale, scaler_min)
+
+    def load_head(self, head_sd, imputer_mean=None, scaler_scale=None, scaler_min=None):
+        n = weights.FEATURE_DIM
+        imputer_mean = np.zeros(n) if imputer_mean is None else imputer_mean
+        scaler_scale = np.ones(n) if scaler_scale is None else scaler_scale
+        scaler_min = np.zeros(n) if scaler_min is None else scaler_min
+        ops.load_head(self.ctx, head_sd, imputer_mean, scaler_scale, scaler_min)
+        self.has_head = True
+
+    def close(self):
+        self.ctx.close()
+
+    # ---------------------------------------------------------------- per-clip image stages
+    def fragments(self, frames, nexts, keep_intermediates=False):
+        """A1-A8 for B pairs of one resolution: -> (ori_frag, merged_frag) [B,224,224,3] u8 BGR."""
+        r = ops.absdiff_patchsum(frames, nexts, want_residual=False, want_gray=True)
+        pos, cnt = ops.topk_patches(r["sums"])
+        ori, diff = ops.gather_fragments(frames, nexts, pos, cnt)
+        flow = ops.farneback(self.ctx, r["gray0"], r["gray1"])
+        _, fsums, minmax = ops.flow_to_rgb(flow, want_rgb=False, want_sums=True)
+        fpos, fcnt = ops.topk_patches(fsums)
+        flow_frag, merged = ops.flow_fragment_merge(flow, minmax, fpos, fcnt, diff, want_flow_frag=keep_intermediates)
+        if keep_intermediates:
+            return dict(ori_frag=ori, diff_frag=diff, merged_frag=merged, flow_frag=flow_frag, flow=flow, positions=pos,
+                        count=cnt, flow_positions=fpos, sums=r["sums"], flow_sums=fsums)
+        return ori, merged
+
+    # --------------------------------------------------------------------------- full path
+    def extract_blocks(self, clips: Sequence[Clip]):
+        """-> dict of per-frame feature matrices stacked over clips + row offsets per clip."""
+        ctx = self.ctx
+        full_rn, full_vt, oris, mers = [], [], [], []
+        full_off, pair_off = [0], [0]
+        for c in clips:
+            tp = c.nexts.shape[0]
+            ori, mer = self.fragments(c.frames[:tp], c.nexts)
+            oris.append(ori)
+            mers.append(mer)
+            full_rn.append(ops.resize_pil(ctx, c.frames, ops.BILINEAR))
+            full_vt.append(ops.resize_pil(ctx, c.frames, ops.LANCZOS))
+            full_off.append(full_off[-1] + c.frames.shape[0])
+            pair_off.append(pair_off[-1] + tp)
+        nf, npair = full_off[-1], pair_off[-1]
+        rn_in = torch.cat(full_rn + oris + mers)
+        vt_in = torch.cat(full_vt + oris + mers)
+        stack, pool = ops.resnet50_features(ctx, rn_in, is_bgr=True, want_stack=True, want_pool=True)
+        vit = ops.vitb16_features(ctx, vt_in, is_bgr=True)
+        dev = self.device
+        return dict(full_resnet=stack[:nf], full_vit=vit[:nf], frag_stack=stack[nf:nf + npair],
+                    frag_pool=pool[nf + npair:], frag_vit_ori=vit[nf:nf + npair], frag_vit_mer=vit[nf + npair:],
+                    full_off=torch.tensor(full_off, dtype=torch.int32, device=dev),
+                    pair_off=torch.tensor(pair_off, dtype=torch.int32, device=dev))
+
+    def extract(self, clips: Sequence[Clip]):
+        """-> features [V, 35203] fp32 on the device (layout of src/demo_test.py:171-175)."""
+        b = self.extract_blocks(clips)
+        return ops.temporal_mean_concat(b["full_resnet"].contiguous(), b["full_vit"].contiguous(), b["frag_stack"].contiguous(),
+                                        b["frag_pool"].contiguous(), b["frag_vit_ori"].contiguous(), b["frag_vit_mer"].contiguous(),
+                                        b["full_off"], b["pair_off"])
+
+    def predict(self, clips: Sequence[Clip], video_type: Optional[str] = None, is_finetune=False):
+        """-> (features [V,35203], scores [V]); scores rescaled like src/demo_test.py:206-219."""
+        if not self.has_head:
+            raise ops._lib.B200VQAError("no regression head loaded")
+        feats = self.extract(clips)
+        score = ops.head_forward(self.ctx, feats)
+        if not is_finetune and video_type in ("youtube_ugc", "konvid_1k"):
+            score = (score / 100.0) * 4.0 + 1.0
+        return feats, score
+
+    def predict_host(self, host_clips: Sequence[Sequence[torch.Tensor]], video_type=None):
+        """End-to-end entry with HOST (pinned) uint8 buffers: H2D copies, full path, D2H of the scores."""
+        clips = [Clip(f.to(self.device, non_blocking=True), n.to(self.device, non_blocking=True)) for f, n in host_clips]
+        feats, score = self.predict(clips, video_type)
+        return feats, score.cpu()
+
+
+def synthetic_clips_on_device(n_clips, H, W, pairs, device, seed=0) -> List[Clip]:
+    """Device-side generator for benchmark inputs (bulk data; parity tests use synth.make_clip on the
+    host instead).  Blurred-noise texture, global shift, one moved block, +-3 noise."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    k = torch.tensor([1, 4, 7, 10, 7, 4, 1], dtype=torch.float32, device=device)
+    k = (k / k.sum())
+    clips = []
+    for _ in range(n_clips):
+        noise = torch.rand((pairs, 3, H + 32, W + 32), generator=g, device=device) * 255.0
+        base = noise
+        for _ in range(3):   # repeated separable binomial blur ~ sigma 3.3
+            base = torch.nn.functional.conv2d(base.reshape(-1, 1, H + 32, W + 32), k.view(1, 1, 1, 7), padding=(0, 3))
+            base = torch.nn.functional.conv2d(base, k.view(1, 1, 7, 1), padding=(3, 0)).reshape(pairs, 3, H + 32, W + 32)
+        base = (base - base.mean()) * 6.0 + 128.0
+        frames = base[:, :, 16:16 + H, 16:16 + W]
+        dx, dy = (int(v) for v in torch.randint(-3, 4, (2,), generator=g, device=device).tolist())
+        moved = torch.roll(base, shifts=(dy, dx), dims=(2, 3)) * 0.5 + torch.roll(base, shifts=(dy, dx + 1), dims=(2, 3)) * 0.5
+        bh, bw = min(130, H // 3), min(160, W // 3)
+        by, bx = 16 + H // 4, 16 + W // 4
+        moved[:, :, by + 5:by + 5 + bh, bx + 10:bx + 10 + bw] = base[:, :, by:by + bh, bx:bx + bw]
+        moved = moved + (torch.rand(moved.shape, generator=g, device=device) * 6.0 - 3.0)
+        nexts = moved[:, :, 16:16 + H, 16:16 + W]
+        to_u8 = lambda t: t.clamp(0, 255).to(torch.uint8).permute(0, 2, 3, 1).contiguous()
+        clips.append(Clip(to_u8(frames), to_u8(nexts)))
+    return clips

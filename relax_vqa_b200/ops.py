@@ -42,6 +42,15 @@ class Context:
     def launches(self):
         return int(self.lib.b200vqa_launch_count(self.h))
 
+    def set_profiling(self, on):
+        check(self.lib.b200vqa_set_profiling(self.h, int(on)), "set_profiling")
+
+    def profile_read(self):
+        """-> (ms spent in tcgen05 GEMM/conv launches, launches, algorithmic FLOPs) since the last read."""
+        ms, n, fl = C.c_double(), C.c_int64(), C.c_double()
+        check(self.lib.b200vqa_profile_read(self.h, C.byref(ms), C.byref(n), C.byref(fl)), "profile_read")
+        return ms.value, n.value, fl.value
+
     def set_gemm_impl(self, impl):
         check(self.lib.b200vqa_set_gemm_impl(self.h, int(impl)), "set_gemm_impl")
 

@@ -1,0 +1,147 @@
+"""End-to-end GPU parity: sampled pairs -> 35,203 vector -> MOS through the public Engine API and
+through the reference-named drop-in functions, against (a) the CPU oracle on the same inputs and
+(b) the UNMODIFIED reference's outputs (tests/golden/ref_video_synth.npz).
+
+Tolerances (north_star): stacked features within 1e-2 (per segment, max|a-b|/rms), MOS within 0.01,
+frame-diff fragments bit-exact; the flow-dependent merged fragment is a float-tolerance stage: report
+its pixel mismatch rate and bound it."""
+import os
+
+import cv2
+import numpy as np
+import pytest
+import torch
+
+from oracle import fragments as F
+from oracle import pipeline as P
+from relax_vqa_b200 import synth, weights
+
+pytestmark = pytest.mark.gpu
+
+BLOCK_SEGS = {
+    "full_resnet": [64, 256, 256, 256, 512, 512, 512, 512, 1024, 1024, 1024, 1024, 2048, 2048, 2048],
+    "full_vit": [768, 768, 768],
+    "frag_resnet": [64, 256, 256, 256, 512, 512, 512, 512, 1024, 1024, 1024, 1024, 2048, 2048, 2048, 2048, 3],
+    "frag_vit": [768] * 6,
+}
+VEC_SEGS = BLOCK_SEGS["full_resnet"] + BLOCK_SEGS["full_vit"] + BLOCK_SEGS["frag_resnet"] + BLOCK_SEGS["frag_vit"]
+
+
+def seg_err(a, b, widths):
+    a, b = np.atleast_2d(a), np.atleast_2d(b)
+    out, o = [], 0
+    for w in widths:
+        ref = b[:, o:o + w]
+        out.append(np.abs(a[:, o:o + w] - ref).max() / max(np.sqrt(np.mean(ref ** 2)), 1e-12))
+        o += w
+    assert o == b.shape[1]
+    return out
+
+
+@pytest.fixture(scope="module")
+def golden(golden_dir):
+    return np.load(os.path.join(golden_dir, "ref_video_synth.npz"))
+
+
+@pytest.fixture(scope="module")
+def engine(golden, golden_dir):
+    from relax_vqa_b200.engine import Engine
+    s = np.load(os.path.join(golden_dir, "konvid_1k_scaler_imputer.npz"))
+    e = Engine(0, weights.seeded_resnet50_state_dict(int(golden["resnet_seed"])), weights.seeded_vitb16_state_dict(int(golden["vit_seed"])),
+               weights.seeded_head_state_dict(int(golden["head_seed"]), swa_format=True), s["imputer_mean"], s["scale"], s["minv"])
+    yield e
+    e.close()
+
+
+def test_video_vector_and_score_vs_reference_golden(engine, golden):
+    from relax_vqa_b200.engine import Clip
+    g = golden
+    fr, nx = synth.make_clip(int(g["clip_seed"]), int(g["H"]), int(g["W"]), int(g["T"]))
+    clip = Clip(torch.from_numpy(fr).cuda(), torch.from_numpy(nx).cuda())
+    b = engine.extract_blocks([clip])
+    got = dict(full_resnet=b["full_resnet"], full_vit=b["full_vit"],
+               frag_resnet=torch.cat([b["frag_stack"], b["frag_pool"]], dim=1),
+               frag_vit=torch.cat([b["frag_vit_ori"], b["frag_vit_mer"]], dim=1))
+    for k, segs in BLOCK_SEGS.items():
+        e = seg_err(got[k].cpu().numpy(), g[k], segs)
+        print(k, "max seg err", max(e))
+        assert max(e) <= 1e-2, (k, e)
+    feats, score = engine.predict([clip], "konvid_1k")
+    assert feats.shape == (1, 35203)
+    assert max(seg_err(feats.cpu().numpy(), g["vector"][None], VEC_SEGS)) <= 1e-2
+    print("score", float(score[0]), "reference", float(g["score"]))
+    assert abs(float(score[0]) - float(g["score"])) <= 0.01
+
+
+def test_fragments_vs_oracle_and_reference(engine, golden_dir):
+    g = np.load(os.path.join(golden_dir, "ref_fragments_synth.npz"))
+    fr, nx = synth.make_clip(int(g["clip_seed"]), int(g["H"]), int(g["W"]), int(g["T"]))
+    out = engine.fragments(torch.from_numpy(fr).cuda(), torch.from_numpy(nx).cuda(), keep_intermediates=True)
+    for t in range(int(g["T"])):
+        assert np.array_equal(out["sums"][t].cpu().numpy().astype(np.float64), g[f"sums{t}"])
+        assert np.array_equal(out["positions"][t].cpu().numpy(), g[f"pos{t}"])
+        assert np.array_equal(out["diff_frag"][t].cpu().numpy(), g[f"diff_frag{t}"])          # bit-exact
+        assert np.array_equal(out["ori_frag"][t].cpu().numpy(), g[f"ori_frag{t}"])            # bit-exact
+        flow_err = np.abs(out["flow"][t].cpu().numpy() - g[f"flow{t}"].astype(np.float32))
+        assert flow_err.max() < 2e-2                                                           # golden flow is stored as fp16
+        mism = (out["merged_frag"][t].cpu().numpy() != g[f"merged{t}"]).any(-1).mean()
+        pos_sym = len(set(map(tuple, out["flow_positions"][t].cpu().numpy().tolist())) ^ set(map(tuple, g[f"flow_pos{t}"].tolist())))
+        print(f"pair {t}: merged-fragment pixel mismatch rate {mism:.5f}, flow patch-set symmetric difference {pos_sym}")
+        assert mism < 0.02 and pos_sym <= 4
+
+
+def test_multi_clip_batch_equals_single(engine):
+    from relax_vqa_b200.engine import Clip
+    clips = []
+    for seed, hw in ((1, (272, 480)), (2, (144, 256)), (3, (272, 480))):
+        fr, nx = synth.make_clip(seed, hw[0], hw[1], 2)
+        clips.append(Clip(torch.from_numpy(fr).cuda(), torch.from_numpy(nx).cuda()))
+    all_feats = engine.extract(clips)
+    for i, c in enumerate(clips):
+        assert torch.equal(engine.extract([c])[0], all_feats[i])        # batch-invariant, bit for bit
+
+
+def test_dropin_functions_match_oracle(engine, tmp_path):
+    from relax_vqa_b200 import main_fragment_layerstack as mfl
+    from relax_vqa_b200 import runtime
+    runtime._engine = engine
+    fr, nx = synth.make_clip(9, 272, 480, 1)
+    residual = cv2.absdiff(nx[0], fr[0])
+    diff = mfl.get_patch_diff(residual, 16)
+    assert diff.dtype == np.float64 and np.array_equal(diff, F.patch_sums(residual))
+    frag, positions = mfl.extract_important_patches(residual, diff)
+    assert positions == F.topk_positions(diff) and np.array_equal(frag, F.gather_fragment(residual, positions))
+    assert np.array_equal(mfl.get_original_frame_patches(fr[0], positions, 16, 224), F.gather_fragment(fr[0], positions))
+    path, imp, pos2 = mfl.process_patches("a/b_1.png", "frame_diff", residual, 16, 224, 196)
+    assert path == "a/b_1_residual_imp.png" and pos2 == positions
+    assert np.array_equal(mfl.merge_fragments(frag, frag[::-1].copy()), cv2.addWeighted(frag, 0.5, frag[::-1].copy(), 0.5, 0))
+    flow = mfl.calc_optical_flow_farneback(fr[0], nx[0])
+    ref_flow = cv2.calcOpticalFlowFarneback(F.bgr2gray(fr[0]), F.bgr2gray(nx[0]), None, 0.5, 3, 15, 3, 5, 1.2, 0)
+    assert np.abs(flow - ref_flow).max() < 2e-3
+    from oracle import farneback as FB
+    assert np.array_equal(mfl.flow_to_rgb(ref_flow), FB.flow_to_rgb(ref_flow))
+    p = str(tmp_path / "vid_1.png")
+    cv2.imwrite(p, fr[0])
+    _, _, vec = mfl.get_deep_feature("resnet50", "vid", p, "original", "layer_stack")
+    rows = mfl.process_video_feature([vec, vec], "resnet50", "layer_stack")
+    assert rows.shape == (2, 13120)
+    _, _, pv = mfl.get_deep_feature("resnet50", "vid", p, "original", "pool")
+    assert mfl.process_video_feature([pv], "resnet50", "pool").shape == (1, 2051)
+    _, _, vv = mfl.get_deep_feature("vit", "vid", p, "original", "pool")
+    assert vv.shape == (2304,)
+    with pytest.raises(ValueError):
+        mfl.get_patch_diff(residual, 8)
+    runtime._engine = None
+
+
+def test_zero_pair_video_does_not_abort_batch(engine):
+    """A video whose sampler produced no pairs gives NaN fragment blocks (imputed by the head), not an abort
+    (the reference dies in np.concatenate)."""
+    from relax_vqa_b200 import ops
+    z = lambda w: torch.zeros((2, w), device="cuda")
+    off_full = torch.tensor([0, 2], dtype=torch.int32, device="cuda")
+    off_pair = torch.tensor([0, 0], dtype=torch.int32, device="cuda")
+    feats = ops.temporal_mean_concat(z(13120), z(2304), z(13120), z(2051), z(2304), z(2304), off_full, off_pair)
+    assert torch.isnan(feats[0, 15424:]).all() and not torch.isnan(feats[0, :15424]).any()
+    score = ops.head_forward(engine.ctx, feats)
+    assert torch.isfinite(score).all()

@@ -2,8 +2,9 @@
 //
 //   D[128 x BN] (fp32, TMEM) += A[128 x 64] (fp16, smem, K-major, SW128) * B[BN x 64]^T
 //
-// Roles (256 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane),
-// warp 2 = TMEM allocator, warps 4-7 = epilogue (TMEM -> registers -> global).
+// Roles (384 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane),
+// warp 2 = TMEM allocator, warps 4-11 = epilogue (TMEM -> registers -> global; two warps per
+// TMEM lane quadrant, each taking half of the accumulator columns).
 // Three pipelines: smem full/empty ring (TMA <-> MMA), TMEM full/empty double buffer
 // (MMA <-> epilogue), static round-robin tile scheduler (tile = blockIdx.x + i*gridDim.x).
 //
@@ -29,7 +30,9 @@ namespace b200vqa {
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
-constexpr int GEMM_THREADS = 256;
+constexpr int GEMM_EPI_WARPS = 8;               // two warps per TMEM lane quadrant
+constexpr int GEMM_EPI_GROUPS = GEMM_EPI_WARPS / 4;
+constexpr int GEMM_THREADS = 128 + 32 * GEMM_EPI_WARPS;
 constexpr int GEMM_MAX_STAGES = 8;
 constexpr uint32_t GEMM_TMEM_COLS = 512;      // two accumulator stages of up to 256 columns
 
@@ -61,7 +64,7 @@ struct GemmParams {
   const float* scale;            // EPI_CONV: [Cout]
   const float* shift;            // EPI_CONV: [Cout]
   const __half* identity;        // EPI_CONV: NHWC fp16 [Nimg][Hout][Wout][Cout] or null
-  float* gap_partial;            // EPI_CONV: [Nimg][tiles_y][Cout] or null
+  float* gap_partial;            // EPI_CONV: [Nimg][tiles_y * GEMM_EPI_GROUPS][Cout] or null
   int gap_raw;                   // pool the raw accumulator (conv1 hook is pre-BN)
 };
 
@@ -121,6 +124,16 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
         "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
       : "r"(taddr));
 }
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major, 128-byte-swizzled operand tile: 8-row groups are 1024 B apart (SBO), LBO unused (1).
@@ -166,7 +179,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < p.stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], GEMM_EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -238,6 +251,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   } else if (warp >= 4) {
     // ================================ epilogue ====================================
     const int q = warp & 3;                           // TMEM lane quadrant of this warp
+    const int grp = (warp - 4) >> 2;                  // which share of the columns this warp drains
     const int row = q * 32 + lane;                    // accumulator row owned by this thread
     int acc = 0; uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -248,56 +262,68 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       if (p.epi == EPI_ROW) {
         const int m = mt * GEMM_BM + row;
         const int n0 = nt * p.block_n;
-        for (int c0 = 0; c0 < p.block_n; c0 += 16) {
-          uint32_t v[16];
-          tmem_ld16(taddr + c0, v);
-          tmem_ld_wait();
-          if (m < p.M) {
+        if ((p.block_n & 31) == 0 && n0 + p.block_n <= p.N) {
+          // fast path: 32-column chunks, interleaved between the two warps of a quadrant
+          for (int c0 = grp * 32; c0 < p.block_n; c0 += 32 * GEMM_EPI_GROUPS) {
+            uint32_t v[32];
+            tmem_ld32(taddr + c0, v);
             const int n = n0 + c0;
-            float f[16];
+            const size_t o = (size_t)m * p.ldo + n;
+            float4 r4[8];
+            if (p.residual && m < p.M) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
-            if (n + 16 <= p.N) {
+              for (int j = 0; j < 8; ++j) r4[j] = *reinterpret_cast<const float4*>(p.residual + o + 4 * j);
+            }
+            tmem_ld_wait();
+            if (m < p.M) {
+              float f[32];
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
               if (p.bias) {
 #pragma unroll
-                for (int j = 0; j < 16; j += 4) {
-                  float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n + j));
+                for (int j = 0; j < 32; j += 4) {
+                  const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n + j));
                   f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
                 }
               }
               if (p.act == ACT_GELU) {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) f[j] = gelu_erf(f[j]);
+                for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
               } else if (p.act == ACT_RELU) {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
+                for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
               }
-              const size_t o = (size_t)m * p.ldo + n;
               if (p.residual) {
 #pragma unroll
-                for (int j = 0; j < 16; j += 4) {
-                  float4 r4 = *reinterpret_cast<const float4*>(p.residual + o + j);
-                  f[j] += r4.x; f[j + 1] += r4.y; f[j + 2] += r4.z; f[j + 3] += r4.w;
-                }
+                for (int j = 0; j < 8; ++j) { f[4 * j] += r4[j].x; f[4 * j + 1] += r4[j].y; f[4 * j + 2] += r4[j].z; f[4 * j + 3] += r4[j].w; }
               }
               if (p.out_is_f32) {
                 float4* op = reinterpret_cast<float4*>(static_cast<float*>(p.out) + o);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) op[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+                for (int j = 0; j < 8; ++j) op[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
               } else {
-                uint32_t h[8];
+                uint32_t h[16];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
+                for (int j = 0; j < 16; ++j) {
                   __half2 t = __floats2half2_rn(f[2 * j], f[2 * j + 1]);
                   h[j] = *reinterpret_cast<uint32_t*>(&t);
                 }
                 uint4* op = reinterpret_cast<uint4*>(static_cast<__half*>(p.out) + o);
-                op[0] = make_uint4(h[0], h[1], h[2], h[3]);
-                op[1] = make_uint4(h[4], h[5], h[6], h[7]);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) op[j] = make_uint4(h[4 * j], h[4 * j + 1], h[4 * j + 2], h[4 * j + 3]);
               }
-            } else {                                   // ragged N tail: scalar path
+            }
+          }
+        } else {
+          // generic path (ragged N / odd tile widths): 16-column chunks, scalar tail
+          for (int c0 = grp * 16; c0 < p.block_n; c0 += 16 * GEMM_EPI_GROUPS) {
+            uint32_t v[16];
+            tmem_ld16(taddr + c0, v);
+            tmem_ld_wait();
+            if (m < p.M) {
+              const int n = n0 + c0;
               for (int j = 0; j < 16 && n + j < p.N; ++j) {
-                float x = f[j] + (p.bias ? p.bias[n + j] : 0.f);
+                float x = __uint_as_float(v[j]) + (p.bias ? p.bias[n + j] : 0.f);
                 if (p.act == ACT_GELU) x = gelu_erf(x); else if (p.act == ACT_RELU) x = fmaxf(x, 0.f);
                 const size_t o = (size_t)m * p.ldo + n + j;
                 if (p.residual) x += p.residual[o];
@@ -307,42 +333,65 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
           }
         }
       } else {
-        // EPI_CONV: this thread owns output channel c; columns are output pixels of the box
+        // EPI_CONV: this thread owns output channel c; columns are output pixels of the box.
+        // The two warps of a quadrant split the pixel columns into contiguous halves (16-px chunks).
         const int c = mt * GEMM_BM + row;
         const bool c_ok = c < p.M;
         const float sc = c_ok ? p.scale[c] : 0.f, sh = c_ok ? p.shift[c] : 0.f;
         const int ty = nt % p.tiles_y, tg = nt / p.tiles_y;
-        __half* out = static_cast<__half*>(p.out);
-        float gsum = 0.f;
-        int g_img = tg * p.tn;                          // image whose pooling partial is being accumulated
-        int x = 0, yrel = 0, n = tg * p.tn;             // running output coordinates of column `pix`
-        for (int c0 = 0; c0 < p.block_n; c0 += 16) {
+        const int per_img = p.tw * p.th;
+        const int nchunks = p.block_n >> 4;
+        const int half = (nchunks + GEMM_EPI_GROUPS - 1) / GEMM_EPI_GROUPS;
+        const int ch_lo = grp * half, ch_hi = min(nchunks, ch_lo + half);
+        __half* __restrict__ out = static_cast<__half*>(p.out);
+        const __half* __restrict__ idt = p.identity;
+        float gs[4] = {0.f, 0.f, 0.f, 0.f};           // pooling partials per image of the tile (tn <= 4)
+        for (int ch = ch_lo; ch < ch_hi; ++ch) {
+          const int pix0 = ch << 4;
           uint32_t v[16];
-          tmem_ld16(taddr + c0, v);
-          tmem_ld_wait();
-          if (c_ok) {
+          tmem_ld16(taddr + pix0, v);
+          // output coordinates of the 16 columns (uniform across the warp)
+          int img = pix0 / per_img;
+          int rem = pix0 - img * per_img;
+          int yrel = rem / p.tw, x = rem - yrel * p.tw;
+          uint32_t off[16];
+          int im[16];
+          __half idv[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              if (n != g_img) {                         // tile spans several images (tn > 1)
-                if (p.gap_partial && g_img < p.Nimg) p.gap_partial[((size_t)g_img * p.tiles_y + ty) * p.M + c] = gsum;
-                g_img = n; gsum = 0.f;
-              }
-              const int y = ty * p.th + yrel;
-              if (x < p.Wout && y < p.Hout && n < p.Nimg) {
-                const float raw = __uint_as_float(v[j]);
-                const size_t o = (((size_t)n * p.Hout + y) * p.Wout + x) * p.M + c;
-                float val = fmaf(raw, sc, sh);
-                if (p.identity) val += __half2float(p.identity[o]);
-                if (p.act == ACT_RELU) val = fmaxf(val, 0.f);
-                gsum += p.gap_raw ? raw : val;
-                out[o] = __float2half_rn(val);
-              }
-              if (++x == p.tw) { x = 0; if (++yrel == p.th) { yrel = 0; ++n; } }
+          for (int j = 0; j < 16; ++j) {
+            const int n = tg * p.tn + img, y = ty * p.th + yrel;
+            const bool ok = c_ok && x < p.Wout && y < p.Hout && n < p.Nimg && img < p.tn;
+            off[j] = ok ? ((uint32_t)((n * p.Hout + y) * p.Wout + x) * (uint32_t)p.M + (uint32_t)c) : 0xFFFFFFFFu;
+            im[j] = img;
+            if (++x == p.tw) { x = 0; if (++yrel == p.th) { yrel = 0; ++img; } }
+          }
+          if (idt) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) idv[j] = off[j] != 0xFFFFFFFFu ? idt[off[j]] : __float2half(0.f);
+          }
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            if (off[j] != 0xFFFFFFFFu) {
+              const float raw = __uint_as_float(v[j]);
+              float val = fmaf(raw, sc, sh);
+              if (idt) val += __half2float(idv[j]);
+              if (p.act == ACT_RELU) val = fmaxf(val, 0.f);
+              const float g = p.gap_raw ? raw : val;
+              gs[0] += im[j] == 0 ? g : 0.f; gs[1] += im[j] == 1 ? g : 0.f;
+              gs[2] += im[j] == 2 ? g : 0.f; gs[3] += im[j] == 3 ? g : 0.f;
+              out[off[j]] = __float2half_rn(val);
             }
           }
         }
-        if (p.gap_partial && c_ok && g_img >= 0 && g_img < p.Nimg)
-          p.gap_partial[((size_t)g_img * p.tiles_y + ty) * p.M + c] = gsum;
+        if (p.gap_partial && c_ok) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int n = tg * p.tn + i;
+            if (i < p.tn && n < p.Nimg)
+              p.gap_partial[((size_t)n * p.tiles_y * GEMM_EPI_GROUPS + ty * GEMM_EPI_GROUPS + grp) * p.M + c] = gs[i];
+          }
+        }
       }
       tcgen05_fence_before();
       __syncwarp();

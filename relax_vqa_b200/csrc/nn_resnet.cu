@@ -110,13 +110,15 @@ k8_gap_finish(HookTable tab, float* __restrict__ stack, int stack_ld, int Nimg) 
 
 // A13: avgpool vector (2048) + [mean, max, std(ddof=0)] over its channels -> [B][2051]
 __global__ void __launch_bounds__(256)
-k8_pool_stats(const float* __restrict__ partial, float inv_hw, float* __restrict__ pool) {
+k8_pool_stats(const float* __restrict__ partial, int slots, float inv_hw, float* __restrict__ pool) {
   __shared__ float red[256];
   __shared__ float s_mean;
   const int n = blockIdx.x, t = threadIdx.x;
   float v[8], sum = 0.f, mx = -INFINITY;
   for (int i = 0; i < 8; ++i) {
-    v[i] = partial[(size_t)n * 2048 + t + i * 256] * inv_hw;
+    float a = 0.f;
+    for (int k = 0; k < slots; ++k) a += partial[((size_t)n * slots + k) * 2048 + t + i * 256];
+    v[i] = a * inv_hw;
     pool[(size_t)n * 2051 + t + i * 256] = v[i];
     sum += v[i]; mx = fmaxf(mx, v[i]);
   }
@@ -293,7 +295,7 @@ extern "C" int b200vqa_resnet50_features(b200vqa_t* h, const uint8_t* img, int B
   // workspace carve-up (bytes), all fp16 NHWC unless noted
   const size_t sz_col = (size_t)nb * 12544 * 192 * 2, sz_c1 = (size_t)nb * 12544 * 64 * 2, sz_big = (size_t)nb * 3136 * 256 * 2;
   const size_t sz_mid = (size_t)nb * 3136 * 128 * 2;
-  const size_t partial_per_img = 56 * 64 + 3 * 14 * 256 + 4 * 7 * 512 + 4 * 1024 + 3 * 2048;
+  const size_t partial_per_img = (size_t)GEMM_EPI_GROUPS * (56 * 64 + 3 * 14 * 256 + 4 * 7 * 512 + 4 * 1024 + 3 * 2048);
   const size_t sz_part = align_up((size_t)nb * partial_per_img * sizeof(float), 256);
   size_t off = 0;
   auto carve = [&](size_t bytes) { size_t o = off; off += align_up(bytes, 1024); return o; };
@@ -321,7 +323,7 @@ extern "C" int b200vqa_resnet50_features(b200vqa_t* h, const uint8_t* img, int B
     const size_t npix = (size_t)n * 12544;
     k8_stem_im2col<<<(unsigned)((npix + 3) / 4), 256, 0, st>>>(im, is_bgr, col, npix);
     VQA_LAUNCH_CHECK();
-    float* gp = add_hook(h->gemm_impl == 1 ? 1 : 56, 64, 12544);
+    float* gp = add_hook(h->gemm_impl == 1 ? 1 : 56 * GEMM_EPI_GROUPS, 64, 12544);
     if ((rc = run_conv(h, rw.stem, col, n, 224, 224, c1, nullptr, 1, gp, 1, st))) return rc;
     {
       const size_t total = (size_t)n * 56 * 56 * 8;
@@ -344,7 +346,7 @@ extern "C" int b200vqa_resnet50_features(b200vqa_t* h, const uint8_t* img, int B
         float* g = nullptr;
         if (b < kStageHooks[s]) {
           const Geo ge = geo_for(Ho);
-          g = add_hook(h->gemm_impl == 1 ? 1 : cdiv(Ho, ge.th), bk.c3.Cout, Ho * Ho);
+          g = add_hook(h->gemm_impl == 1 ? 1 : cdiv(Ho, ge.th) * GEMM_EPI_GROUPS, bk.c3.Cout, Ho * Ho);
         }
         if ((rc = run_conv(h, bk.c3, bb, n, Ho, Ho, y, idt, 1, g, 0, st))) return rc;
         __half* t = x; x = y; y = t;
@@ -356,8 +358,8 @@ extern "C" int b200vqa_resnet50_features(b200vqa_t* h, const uint8_t* img, int B
       VQA_LAUNCH_CHECK();
     }
     if (pool) {
-      // layer4[2] is the last hook; with tiles_y == 1 its partial sums are the avgpool numerators
-      k8_pool_stats<<<n, 256, 0, st>>>(tab.h[14].partial, tab.h[14].inv_hw, pool + (size_t)b0 * B200VQA_RESNET_POOL);
+      // layer4[2] is the last hook; its partial slots summed in order are the avgpool numerators
+      k8_pool_stats<<<n, 256, 0, st>>>(tab.h[14].partial, tab.h[14].tiles_y, tab.h[14].inv_hw, pool + (size_t)b0 * B200VQA_RESNET_POOL);
       VQA_LAUNCH_CHECK();
     }
   }

@@ -4,7 +4,7 @@
 // Data layout in HBM (per level, SoA so that every access is a coalesced float stream):
 //   I   [2][B][h][w]      f32  blurred + resized images
 //   R   [2][B][5][h][w]   f32  polynomial expansion coefficients (y, x, yy, xx, xy)
-//   M   [B][5][h][w]      f32  structure-tensor entries
+//   M                     structure-tensor entries: shared memory only (fused iteration kernel)
 //   flow[B][h][w][2]      f32  (dx, dy), ping-pong between levels
 #include <math.h>
 #include <vector>
@@ -13,7 +13,7 @@
 namespace b200vqa {
 
 struct Taps { float t[19]; int ksize; };
-struct PolyConsts { float g[6], xg[6], xxg[6]; double ig11, ig03, ig33, ig55; };   // index k = 0..5 (symmetric)
+struct PolyConsts { float g[6], xg[6], xxg[6]; float ig11, ig03, ig33, ig55; };   // index k = 0..5 (symmetric)
 
 __device__ __forceinline__ int reflect101(int i, int n) {
   if (i < 0) i = -i;
@@ -21,49 +21,74 @@ __device__ __forceinline__ int reflect101(int i, int n) {
   return i;
 }
 
-// ---- (a) horizontal Gaussian on the full-resolution uint8 image -> f32
-__global__ void __launch_bounds__(256)
-k4_blur_h(const uint8_t* __restrict__ gray, int H, int W, Taps taps, float* __restrict__ out) {
-  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
-  if (x >= W) return;
-  const size_t rowoff = ((size_t)blockIdx.z * H + y) * W;
-  const uint8_t* row = gray + rowoff;
-  const int r = taps.ksize >> 1;
-  float acc = 0.f;
-  for (int k = 0; k < taps.ksize; ++k) acc += taps.t[k] * (float)row[reflect101(x + k - r, W)];
-  out[rowoff + x] = acc;
+// ---- (a+b) fused pyramid level: GaussianBlur(full-res uint8, ksize, sigma) sampled by cv::resize
+// INTER_LINEAR at the level's pixel centres.  One block = 32 x 8 outputs; the source window is staged in
+// shared memory (uint8), blurred horizontally only at the <= 64 columns the bilinear taps need (f32, smem),
+// then blurred vertically at the <= 2 rows each output needs.  Row filter before column filter, like OpenCV.
+constexpr int PY_TX = 32, PY_TY = 8;
+__device__ __forceinline__ void lin_split(int d, double scale, int n_in, bool same, int& i0, int& i1, float& a) {
+  if (same) { i0 = i1 = d; a = 0.f; return; }
+  const double s = (d + 0.5) * scale - 0.5;
+  int f = (int)floor(s);
+  a = (float)(s - f);
+  if (f < 0) { f = 0; a = 0.f; }
+  i0 = f; i1 = f + 1;
+  if (f >= n_in - 1) { i0 = i1 = n_in - 1; a = 0.f; }
 }
 
-// ---- (b) vertical Gaussian + bilinear resize (cv::resize INTER_LINEAR, half-pixel centres)
 __global__ void __launch_bounds__(256)
-k4_blur_v_resize(const float* __restrict__ tmp, int H, int W, Taps taps, int h, int w, double sx, double sy,
-                 float* __restrict__ out) {
-  const int xo = blockIdx.x * blockDim.x + threadIdx.x, yo = blockIdx.y;
-  if (xo >= w) return;
-  const float* img = tmp + (size_t)blockIdx.z * H * W;
+k4_pyr_level(const uint8_t* __restrict__ gray0, const uint8_t* __restrict__ gray1, int B, int H, int W, Taps taps, int h, int w,
+             double sx, double sy, float* __restrict__ out) {
+  extern __shared__ __align__(16) uint8_t py_smem[];
   const int r = taps.ksize >> 1;
-  int x0, x1, y0, y1; float ax, ay;
-  if (h == H && w == W) { x0 = x1 = xo; y0 = y1 = yo; ax = ay = 0.f; }
-  else {
-    // source coordinates in double then split, as in oracle/farneback.py::_linear_coords
-    double s = (xo + 0.5) * sx - 0.5; int f = (int)floor(s); float a = (float)(s - f);
-    if (f < 0) { f = 0; a = 0.f; } x0 = f; x1 = f + 1; if (f >= W - 1) { x0 = x1 = W - 1; a = 0.f; } ax = a;
-    s = (yo + 0.5) * sy - 0.5; f = (int)floor(s); a = (float)(s - f);
-    if (f < 0) { f = 0; a = 0.f; } y0 = f; y1 = f + 1; if (f >= H - 1) { y0 = y1 = H - 1; a = 0.f; } ay = a;
+  const bool same = (h == H && w == W);
+  const int z = blockIdx.z;
+  const uint8_t* img = (z < B ? gray0 + (size_t)z * H * W : gray1 + (size_t)(z - B) * H * W);
+  const int xo0 = blockIdx.x * PY_TX, yo0 = blockIdx.y * PY_TY;
+  const int xo_last = min(xo0 + PY_TX, w) - 1, yo_last = min(yo0 + PY_TY, h) - 1;
+  int i0, i1; float a;
+  lin_split(xo0, sx, W, same, i0, i1, a);      const int x_lo = i0 - r;
+  lin_split(xo_last, sx, W, same, i0, i1, a);  const int x_hi = i1 + r;
+  lin_split(yo0, sy, H, same, i0, i1, a);      const int y_lo = i0 - r;
+  lin_split(yo_last, sy, H, same, i0, i1, a);  const int y_hi = i1 + r;
+  const int sw = x_hi - x_lo + 1, sh = y_hi - y_lo + 1;
+  const int sw_p = (sw + 3) & ~3;
+  uint8_t* src = py_smem;                                         // [sh][sw_p] uint8
+  float* hs = reinterpret_cast<float*>(py_smem + (((size_t)sh * sw_p + 15) & ~(size_t)15));   // [sh][2*PY_TX] f32
+  const int tid = threadIdx.x;
+  for (int i = tid; i < sh * sw; i += 256) {
+    const int ty = i / sw, tx = i - ty * sw;
+    src[ty * sw_p + tx] = img[(size_t)reflect101(y_lo + ty, H) * W + reflect101(x_lo + tx, W)];
   }
-  float b00 = 0.f, b01 = 0.f, b10 = 0.f, b11 = 0.f;
-  for (int k = 0; k < taps.ksize; ++k) {
-    const float t = taps.t[k];
-    const float* ra = img + (size_t)reflect101(y0 + k - r, H) * W;
-    b00 += t * ra[x0]; b01 += t * ra[x1];
-    if (y1 != y0) {
-      const float* rb = img + (size_t)reflect101(y1 + k - r, H) * W;
-      b10 += t * rb[x0]; b11 += t * rb[x1];
-    }
+  __syncthreads();
+  // horizontal pass at the needed columns: column slot 2j / 2j+1 = left / right tap of output xo0 + j
+  for (int i = tid; i < sh * 2 * PY_TX; i += 256) {
+    const int ty = i / (2 * PY_TX), slot = i - ty * (2 * PY_TX);
+    const int xo = min(xo0 + (slot >> 1), w - 1);
+    lin_split(xo, sx, W, same, i0, i1, a);
+    const int xc = ((slot & 1) ? i1 : i0) - r - x_lo;              // window start inside the tile
+    const uint8_t* row = src + ty * sw_p + xc;
+    float acc = 0.f;
+    for (int k = 0; k < taps.ksize; ++k) acc += taps.t[k] * (float)row[k];
+    hs[i] = acc;
   }
-  if (y1 == y0) { b10 = b00; b11 = b01; }
-  const float top = b00 * (1.f - ax) + b01 * ax, bot = b10 * (1.f - ax) + b11 * ax;
-  out[((size_t)blockIdx.z * h + yo) * w + xo] = top * (1.f - ay) + bot * ay;
+  __syncthreads();
+  const int tx = tid & (PY_TX - 1), ty = tid / PY_TX;
+  const int xo = xo0 + tx, yo = yo0 + ty;
+  if (xo < w && yo < h) {
+    float ax, ay; int xa, xb, ya, yb;
+    lin_split(xo, sx, W, same, xa, xb, ax);
+    lin_split(yo, sy, H, same, ya, yb, ay);
+    const float* c0 = hs + (size_t)(ya - r - y_lo) * (2 * PY_TX) + 2 * tx;
+    float b00 = 0.f, b01 = 0.f, b10 = 0.f, b11 = 0.f;
+    for (int k = 0; k < taps.ksize; ++k) { const float t = taps.t[k]; b00 += t * c0[k * 2 * PY_TX]; b01 += t * c0[k * 2 * PY_TX + 1]; }
+    if (yb != ya) {
+      const float* c1 = hs + (size_t)(yb - r - y_lo) * (2 * PY_TX) + 2 * tx;
+      for (int k = 0; k < taps.ksize; ++k) { const float t = taps.t[k]; b10 += t * c1[k * 2 * PY_TX]; b11 += t * c1[k * 2 * PY_TX + 1]; }
+    } else { b10 = b00; b11 = b01; }
+    const float top = b00 * (1.f - ax) + b01 * ax, bot = b10 * (1.f - ax) + b11 * ax;
+    out[((size_t)z * h + yo) * w + xo] = top * (1.f - ay) + bot * ay;
+  }
 }
 
 // ---- (c) polynomial expansion: I [h][w] -> R planes.  Tile 32 x 16, halo 5, smem staged.
@@ -98,7 +123,8 @@ k4_polyexp(const float* __restrict__ I, int h, int w, PolyConsts pc, float* __re
     v0[ty][tx] = r0; v1[ty][tx] = r1; v2[ty][tx] = r2;
   }
   __syncthreads();
-  // horizontal pass (f64 accumulators, as OpenCV); columns beyond the image replicate the edge
+  // horizontal pass.  OpenCV accumulates this pass in f64; f32 changes the flow by < 1e-5 px (measured, see
+  // DESIGN.md) and avoids the quarter-rate f32->f64 conversions.  Columns beyond the image replicate the edge
   // column of the *vertical* result - which is what the clamped tile load produced.
   const size_t plane = (size_t)h * w;
   float* Rb = R + (size_t)blockIdx.z * 5 * plane;
@@ -107,11 +133,11 @@ k4_polyexp(const float* __restrict__ I, int h, int w, PolyConsts pc, float* __re
     const int gx = x0 + tx, gy = y0 + ty;
     if (gx >= w || gy >= h) continue;
     const int c = tx + PE_N;
-    double b1 = (double)v0[ty][c] * pc.g[0], b2 = 0, b3 = (double)v1[ty][c] * pc.g[0], b4 = 0, b5 = (double)v2[ty][c] * pc.g[0], b6 = 0;
+    float b1 = v0[ty][c] * pc.g[0], b2 = 0.f, b3 = v1[ty][c] * pc.g[0], b4 = 0.f, b5 = v2[ty][c] * pc.g[0], b6 = 0.f;
 #pragma unroll
     for (int k = 1; k <= PE_N; ++k) {
-      const double p0 = v0[ty][c + k], m0 = v0[ty][c - k], p1 = v1[ty][c + k], m1 = v1[ty][c - k], p2 = v2[ty][c + k], m2 = v2[ty][c - k];
-      const double tg = p0 + m0;
+      const float p0 = v0[ty][c + k], m0 = v0[ty][c - k], p1 = v1[ty][c + k], m1 = v1[ty][c - k], p2 = v2[ty][c + k], m2 = v2[ty][c - k];
+      const float tg = p0 + m0;
       b1 += tg * pc.g[k];
       b4 += tg * pc.xxg[k];
       b2 += (p0 - m0) * pc.xg[k];
@@ -120,15 +146,16 @@ k4_polyexp(const float* __restrict__ I, int h, int w, PolyConsts pc, float* __re
       b5 += (p2 + m2) * pc.g[k];
     }
     const size_t o = (size_t)gy * w + gx;
-    Rb[o] = (float)(b3 * pc.ig11);
-    Rb[plane + o] = (float)(b2 * pc.ig11);
-    Rb[2 * plane + o] = (float)(b1 * pc.ig03 + b5 * pc.ig33);
-    Rb[3 * plane + o] = (float)(b1 * pc.ig03 + b4 * pc.ig33);
-    Rb[4 * plane + o] = (float)(b6 * pc.ig55);
+    Rb[o] = b3 * pc.ig11;
+    Rb[plane + o] = b2 * pc.ig11;
+    Rb[2 * plane + o] = b1 * pc.ig03 + b5 * pc.ig33;
+    Rb[3 * plane + o] = b1 * pc.ig03 + b4 * pc.ig33;
+    Rb[4 * plane + o] = b6 * pc.ig55;
   }
 }
 
-// ---- (d) FarnebackUpdateMatrices
+// ---- (d+e) one Farneback iteration, fused: FarnebackUpdateMatrices on the 46 x 46 halo of a 32 x 32 tile
+// (M never touches HBM), 15 x 15 box sums with replicate border, 2 x 2 solve.  flow_in -> flow_out.
 __device__ __forceinline__ float border_w(int i, int n) {
   float s = 1.f;
   if (i < 5) s *= (i < 2 ? 0.14f : 0.4472f);
@@ -137,100 +164,102 @@ __device__ __forceinline__ float border_w(int i, int n) {
   return s;
 }
 
+constexpr int BX_T = 32, BX_M = 7, BX_IN = BX_T + 2 * BX_M, BX_LD = BX_IN + 1;     // 46, 47
+constexpr int BX_SMEM = (5 * BX_IN * BX_LD + 5 * BX_T * BX_LD) * 4;
 __global__ void __launch_bounds__(256)
-k4_update_matrices(const float* __restrict__ R0, const float* __restrict__ R1, const float* __restrict__ flow, int h, int w,
-                   float* __restrict__ M) {
-  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
-  if (x >= w) return;
-  const size_t plane = (size_t)h * w, o = (size_t)y * w + x;
-  const float* r0 = R0 + (size_t)blockIdx.z * 5 * plane;
-  const float* r1 = R1 + (size_t)blockIdx.z * 5 * plane;
-  const float2 d = reinterpret_cast<const float2*>(flow)[(size_t)blockIdx.z * plane + o];
-  const float dx = d.x, dy = d.y;
-  float fx = (float)x + dx, fy = (float)y + dy;
-  const int x1 = (int)floorf(fx), y1 = (int)floorf(fy);
-  fx -= (float)x1; fy -= (float)y1;
-  float r2, r3, r4, r5, r6;
-  const float a4 = r0[2 * plane + o], a5 = r0[3 * plane + o], a6 = r0[4 * plane + o];
-  if ((unsigned)x1 < (unsigned)(w - 1) && (unsigned)y1 < (unsigned)(h - 1)) {
-    const float a00 = (1.f - fx) * (1.f - fy), a01 = fx * (1.f - fy), a10 = (1.f - fx) * fy, a11 = fx * fy;
-    const size_t q = (size_t)y1 * w + x1;
-#define BIL(c) (a00 * r1[(c) * plane + q] + a01 * r1[(c) * plane + q + 1] + a10 * r1[(c) * plane + q + w] + a11 * r1[(c) * plane + q + w + 1])
-    r2 = BIL(0); r3 = BIL(1); r4 = BIL(2); r5 = BIL(3); r6 = BIL(4);
-#undef BIL
-    r4 = (a4 + r4) * 0.5f; r5 = (a5 + r5) * 0.5f; r6 = (a6 + r6) * 0.25f;
-  } else {
-    r2 = r3 = 0.f; r4 = a4; r5 = a5; r6 = a6 * 0.5f;
-  }
-  r2 = (r0[o] - r2) * 0.5f;
-  r3 = (r0[plane + o] - r3) * 0.5f;
-  r2 += r4 * dy + r6 * dx;
-  r3 += r6 * dy + r5 * dx;
-  if ((unsigned)(x - 5) >= (unsigned)(w - 10) || (unsigned)(y - 5) >= (unsigned)(h - 10)) {
-    const float s = border_w(y, h) * border_w(x, w);     // (sy*sx) as in the oracle
-    r2 *= s; r3 *= s; r4 *= s; r5 *= s; r6 *= s;
-  }
-  float* m = M + (size_t)blockIdx.z * 5 * plane;
-  m[o] = r4 * r4 + r6 * r6;
-  m[plane + o] = (r4 + r5) * r6;
-  m[2 * plane + o] = r5 * r5 + r6 * r6;
-  m[3 * plane + o] = r4 * r2 + r6 * r3;
-  m[4 * plane + o] = r6 * r2 + r5 * r3;
-}
-
-// ---- (e) 15x15 box sum (f64, replicate border) + 2x2 solve.  Tile 32 x 32 outputs.
-constexpr int BX_T = 32, BX_M = 7, BX_IN = BX_T + 2 * BX_M;     // 46
-__global__ void __launch_bounds__(256)
-k4_box_solve(const float* __restrict__ M, int h, int w, float* __restrict__ flow) {
-  extern __shared__ double vs[];                    // [5][BX_T][BX_IN + 1]
+k4_flow_iter(const float* __restrict__ R0, const float* __restrict__ R1, const float* __restrict__ flow_in, int h, int w,
+             float* __restrict__ flow_out) {
+  extern __shared__ float bx_smem[];
+  float* Ms = bx_smem;                               // [5][46][47]
+  float* Vs = bx_smem + 5 * BX_IN * BX_LD;           // [5][32][47]
   const int x0 = blockIdx.x * BX_T, y0 = blockIdx.y * BX_T;
   const size_t plane = (size_t)h * w;
-  const float* m = M + (size_t)blockIdx.z * 5 * plane;
+  const float* r0 = R0 + (size_t)blockIdx.z * 5 * plane;
+  const float* r1 = R1 + (size_t)blockIdx.z * 5 * plane;
+  const float2* fin = reinterpret_cast<const float2*>(flow_in) + (size_t)blockIdx.z * plane;
   const int tid = threadIdx.x;
-  // phase 1: vertical sliding sums; task = (channel, column) : 5 * 46 = 230 tasks
+  // phase A: structure-tensor entries at the (replicate-clamped) halo pixels
+  for (int i = tid; i < BX_IN * BX_IN; i += 256) {
+    const int ty = i / BX_IN, tx = i - ty * BX_IN;
+    const int x = min(max(x0 + tx - BX_M, 0), w - 1), y = min(max(y0 + ty - BX_M, 0), h - 1);
+    const size_t o = (size_t)y * w + x;
+    const float2 d = fin[o];
+    const float dx = d.x, dy = d.y;
+    float fx = (float)x + dx, fy = (float)y + dy;
+    const int x1 = (int)floorf(fx), y1 = (int)floorf(fy);
+    fx -= (float)x1; fy -= (float)y1;
+    float r2, r3, r4, r5, r6;
+    const float a4 = r0[2 * plane + o], a5 = r0[3 * plane + o], a6 = r0[4 * plane + o];
+    if ((unsigned)x1 < (unsigned)(w - 1) && (unsigned)y1 < (unsigned)(h - 1)) {
+      const float a00 = (1.f - fx) * (1.f - fy), a01 = fx * (1.f - fy), a10 = (1.f - fx) * fy, a11 = fx * fy;
+      const size_t q = (size_t)y1 * w + x1;
+#define BIL(c) (a00 * r1[(c) * plane + q] + a01 * r1[(c) * plane + q + 1] + a10 * r1[(c) * plane + q + w] + a11 * r1[(c) * plane + q + w + 1])
+      r2 = BIL(0); r3 = BIL(1); r4 = BIL(2); r5 = BIL(3); r6 = BIL(4);
+#undef BIL
+      r4 = (a4 + r4) * 0.5f; r5 = (a5 + r5) * 0.5f; r6 = (a6 + r6) * 0.25f;
+    } else {
+      r2 = r3 = 0.f; r4 = a4; r5 = a5; r6 = a6 * 0.5f;
+    }
+    r2 = (r0[o] - r2) * 0.5f;
+    r3 = (r0[plane + o] - r3) * 0.5f;
+    r2 += r4 * dy + r6 * dx;
+    r3 += r6 * dy + r5 * dx;
+    if ((unsigned)(x - 5) >= (unsigned)(w - 10) || (unsigned)(y - 5) >= (unsigned)(h - 10)) {
+      const float s = border_w(y, h) * border_w(x, w);
+      r2 *= s; r3 *= s; r4 *= s; r5 *= s; r6 *= s;
+    }
+    float* m = Ms + ty * BX_LD + tx;
+    m[0] = r4 * r4 + r6 * r6;
+    m[BX_IN * BX_LD] = (r4 + r5) * r6;
+    m[2 * BX_IN * BX_LD] = r5 * r5 + r6 * r6;
+    m[3 * BX_IN * BX_LD] = r4 * r2 + r6 * r3;
+    m[4 * BX_IN * BX_LD] = r6 * r2 + r5 * r3;
+  }
+  __syncthreads();
+  // phase B: vertical sliding sums (f32; the walk is only 32 rows long, error ~ that of a direct 15-tap sum)
   if (tid < 5 * BX_IN) {
-    const int c = tid / BX_IN, j = tid % BX_IN;
-    const int gx = min(max(x0 + j - BX_M, 0), w - 1);
-    const float* col = m + (size_t)c * plane + gx;
-    double s = 0.0;
-    for (int i = -BX_M; i <= BX_M; ++i) s += (double)col[(size_t)min(max(y0 + i, 0), h - 1) * w];
-    double* dst = vs + ((size_t)c * BX_T) * (BX_IN + 1) + j;
-    for (int r = 0; r < BX_T; ++r) {
-      dst[(size_t)r * (BX_IN + 1)] = s;
-      const int yin = min(max(y0 + r + BX_M + 1, 0), h - 1), yout = min(max(y0 + r - BX_M, 0), h - 1);
-      s += (double)col[(size_t)yin * w] - (double)col[(size_t)yout * w];
+    const int c = tid / BX_IN, j = tid - c * BX_IN;
+    const float* col = Ms + (size_t)c * BX_IN * BX_LD + j;
+    float* dst = Vs + (size_t)c * BX_T * BX_LD + j;
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 15; ++i) s += col[i * BX_LD];
+    dst[0] = s;
+    for (int rr = 1; rr < BX_T; ++rr) {
+      s += col[(rr + 14) * BX_LD] - col[(rr - 1) * BX_LD];
+      dst[rr * BX_LD] = s;
     }
   }
   __syncthreads();
-  // phase 2: horizontal sums over 8-column segments; task = (row, segment): 32 * 4 = 128 tasks
-  if (tid < BX_T * 4) {
-    const int r = tid >> 2, seg = tid & 3;
-    const int gy = y0 + r;
-    if (gy < h) {
-      double g[5];
+  // phase C: horizontal sums over 4-column segments + solve (f64, as OpenCV): task = (row, segment)
+  {
+    const int rr = tid >> 3, seg = tid & 7;
+    const int gy = y0 + rr;
+    float g[5];
+#pragma unroll
+    for (int c = 0; c < 5; ++c) {
+      const float* row = Vs + ((size_t)c * BX_T + rr) * BX_LD + seg * 4;
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < 15; ++i) s += row[i];
+      g[c] = s;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int gx = x0 + seg * 4 + k;
+      if (gx < w && gy < h) {
+        const double sc = 1.0 / 225.0;
+        const double g11 = g[0] * sc, g12 = g[1] * sc, g22 = g[2] * sc, h1 = g[3] * sc, h2 = g[4] * sc;
+        const double idet = 1.0 / (g11 * g22 - g12 * g12 + 1e-3);
+        float2 f;
+        f.x = (float)((g11 * h2 - g12 * h1) * idet);
+        f.y = (float)((g22 * h1 - g12 * h2) * idet);
+        reinterpret_cast<float2*>(flow_out)[(size_t)blockIdx.z * plane + (size_t)gy * w + gx] = f;
+      }
 #pragma unroll
       for (int c = 0; c < 5; ++c) {
-        const double* row = vs + ((size_t)c * BX_T + r) * (BX_IN + 1) + seg * 8;
-        double s = 0.0;
-        for (int i = 0; i < 15; ++i) s += row[i];
-        g[c] = s;
-      }
-      for (int k = 0; k < 8; ++k) {
-        const int gx = x0 + seg * 8 + k;
-        if (gx < w) {
-          const double sc = 1.0 / 225.0;
-          const double g11 = g[0] * sc, g12 = g[1] * sc, g22 = g[2] * sc, h1 = g[3] * sc, h2 = g[4] * sc;
-          const double idet = 1.0 / (g11 * g22 - g12 * g12 + 1e-3);
-          float2 f;
-          f.x = (float)((g11 * h2 - g12 * h1) * idet);
-          f.y = (float)((g22 * h1 - g12 * h2) * idet);
-          reinterpret_cast<float2*>(flow)[(size_t)blockIdx.z * plane + (size_t)gy * w + gx] = f;
-        }
-#pragma unroll
-        for (int c = 0; c < 5; ++c) {
-          const double* row = vs + ((size_t)c * BX_T + r) * (BX_IN + 1) + seg * 8 + k;
-          g[c] += row[15] - row[0];
-        }
+        const float* row = Vs + ((size_t)c * BX_T + rr) * BX_LD + seg * 4 + k;
+        g[c] += row[15] - row[0];
       }
     }
   }
@@ -437,7 +466,7 @@ static PolyConsts poly_consts() {           // FarnebackPrepareGaussian(n = 5, s
   invert6(G, inv);
   PolyConsts pc;
   for (int k = 0; k <= n; ++k) { pc.g[k] = g[n + k]; pc.xg[k] = xg[n + k]; pc.xxg[k] = xxg[n + k]; }
-  pc.ig11 = inv[1][1]; pc.ig03 = inv[0][3]; pc.ig33 = inv[3][3]; pc.ig55 = inv[5][5];
+  pc.ig11 = (float)inv[1][1]; pc.ig03 = (float)inv[0][3]; pc.ig33 = (float)inv[3][3]; pc.ig55 = (float)inv[5][5];
   return pc;
 }
 
@@ -466,64 +495,60 @@ extern "C" int b200vqa_farneback(b200vqa_t* h, const uint8_t* gray0, const uint8
   CtxScope scope(h);
   cudaStream_t st = as_stream(stream);
   const size_t P = (size_t)H * W;
-  // workspace (float): tmp [B][P] | I [2][B][P] | R [2][B][5][P] | M [B][5][P] | flowA, flowB [B][Pq][2]
-  // (Pq = largest non-final level, about P/4)
+  // workspace (float): I [2][B][P] | R [2][B][5][P] | flowA, flowB [B][P][2]
   const std::vector<Level> plan = pyramid_plan(H, W);
-  size_t Pq = 1;
-  for (size_t li = 0; li + 1 < plan.size(); ++li) Pq = std::max(Pq, (size_t)plan[li].h * plan[li].w);
-  const size_t floats = (size_t)B * (P * (1 + 2 + 10 + 5) + Pq * 4);
+  const size_t floats = (size_t)B * P * (2 + 10 + 4);
   int rc = h->ws_flow.reserve(floats * sizeof(float));
   if (rc) return rc;
-  float* tmp = static_cast<float*>(h->ws_flow.ptr);
-  float* I = tmp + (size_t)B * P;
+  float* I = static_cast<float*>(h->ws_flow.ptr);
   float* R = I + 2 * (size_t)B * P;
-  float* M = R + 10 * (size_t)B * P;
-  float* flowA = M + 5 * (size_t)B * P;
-  float* flowB = flowA + 2 * (size_t)B * Pq;
+  float* flowA = R + 10 * (size_t)B * P;
+  float* flowB = flowA + 2 * (size_t)B * P;
   static const PolyConsts pc = poly_consts();
   static bool attr_done = false;
   if (!attr_done) {
-    VQA_CUDA(cudaFuncSetAttribute(k4_box_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(5 * BX_T * (BX_IN + 1) * sizeof(double))));
+    VQA_CUDA(cudaFuncSetAttribute(k4_flow_iter, cudaFuncAttributeMaxDynamicSharedMemorySize, BX_SMEM));
+    VQA_CUDA(cudaFuncSetAttribute(k4_pyr_level, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     attr_done = true;
   }
-  float* cur = nullptr;          // flow of the previous (coarser) level
+  float* prev = nullptr;         // flow of the previous (coarser) level
   int ph = 0, pw = 0;
   for (size_t li = 0; li < plan.size(); ++li) {
     const Level& L = plan[li];
     const bool last = li + 1 == plan.size();
-    float* lvl_flow = last ? flow : (cur == flowA ? flowB : flowA);
     const Taps taps = gaussian_taps(L.ksize, L.sigma);
     const size_t lp = (size_t)L.h * L.w;
     float* R0 = R; float* R1 = R + (size_t)B * 5 * lp;
-    for (int im = 0; im < 2; ++im) {
-      k4_blur_h<<<dim3(cdiv(W, 256), H, B), 256, 0, st>>>(im ? gray1 : gray0, H, W, taps, tmp);
+    {
+      const double sx = (double)W / L.w, sy = (double)H / L.h;
+      // shared-memory window: uint8 source tile + f32 horizontally blurred columns
+      const int sw = (int)(PY_TX * sx) + L.ksize + 4, sh = (int)(PY_TY * sy) + L.ksize + 4;
+      const size_t smem = (((size_t)sh * ((sw + 3) & ~3) + 15) & ~(size_t)15) + (size_t)sh * 2 * PY_TX * sizeof(float);
+      if (smem > 100 * 1024) return B200VQA_EINVAL;
+      k4_pyr_level<<<dim3(cdiv(L.w, PY_TX), cdiv(L.h, PY_TY), 2 * B), 256, smem, st>>>(gray0, gray1, B, H, W, taps, L.h, L.w, sx, sy, I);
       VQA_LAUNCH_CHECK();
-      float* Iim = I + (size_t)im * B * lp;
-      k4_blur_v_resize<<<dim3(cdiv(L.w, 256), L.h, B), 256, 0, st>>>(tmp, H, W, taps, L.h, L.w, (double)W / L.w, (double)H / L.h, Iim);
-      VQA_LAUNCH_CHECK();
-      k4_polyexp<<<dim3(cdiv(L.w, PE_TW), cdiv(L.h, PE_TH), B), 256, 0, st>>>(Iim, L.h, L.w, pc, im ? R1 : R0);
+      // I holds [2B][h][w]; R0 = expansion of images 0..B-1, R1 of B..2B-1 (contiguous)
+      k4_polyexp<<<dim3(cdiv(L.w, PE_TW), cdiv(L.h, PE_TH), 2 * B), 256, 0, st>>>(I, L.h, L.w, pc, R0);
       VQA_LAUNCH_CHECK();
     }
-    if (!cur) {
-      VQA_CUDA(cudaMemsetAsync(lvl_flow, 0, (size_t)B * lp * 2 * sizeof(float), st));
+    float* fin = flowA;
+    if (!prev) {
+      VQA_CUDA(cudaMemsetAsync(fin, 0, (size_t)B * lp * 2 * sizeof(float), st));
       count_launch();
     } else {
-      k4_flow_upsample<<<dim3(cdiv(L.w, 256), L.h, B), 256, 0, st>>>(cur, ph, pw, L.h, L.w, (double)pw / L.w, (double)ph / L.h, lvl_flow);
+      fin = (prev == flowA) ? flowB : flowA;
+      k4_flow_upsample<<<dim3(cdiv(L.w, 256), L.h, B), 256, 0, st>>>(prev, ph, pw, L.h, L.w, (double)pw / L.w, (double)ph / L.h, fin);
       VQA_LAUNCH_CHECK();
     }
-    const dim3 gpix(cdiv(L.w, 256), L.h, B), gbox(cdiv(L.w, BX_T), cdiv(L.h, BX_T), B);
-    const size_t box_smem = 5 * BX_T * (BX_IN + 1) * sizeof(double);
-    k4_update_matrices<<<gpix, 256, 0, st>>>(R0, R1, lvl_flow, L.h, L.w, M);
-    VQA_LAUNCH_CHECK();
+    const dim3 gbox(cdiv(L.w, BX_T), cdiv(L.h, BX_T), B);
+    float* fout = nullptr;
     for (int it = 0; it < 3; ++it) {
-      k4_box_solve<<<gbox, 256, box_smem, st>>>(M, L.h, L.w, lvl_flow);
+      fout = (last && it == 2) ? flow : (fin == flowA ? flowB : flowA);
+      k4_flow_iter<<<gbox, 256, BX_SMEM, st>>>(R0, R1, fin, L.h, L.w, fout);
       VQA_LAUNCH_CHECK();
-      if (it < 2) {
-        k4_update_matrices<<<gpix, 256, 0, st>>>(R0, R1, lvl_flow, L.h, L.w, M);
-        VQA_LAUNCH_CHECK();
-      }
+      fin = fout;
     }
-    cur = lvl_flow; ph = L.h; pw = L.w;
+    prev = fout; ph = L.h; pw = L.w;
   }
   return B200VQA_OK;
 }

@@ -3,7 +3,7 @@
 // Algorithm restated from OpenCV's optflowgf.cpp as pinned by oracle/farneback.py.
 // Data layout in HBM (per level, SoA so that every access is a coalesced float stream):
 //   I   [2][B][h][w]      f32  blurred + resized images
-//   R   [2][B][5][h][w]   f32  polynomial expansion coefficients (y, x, yy, xx, xy)
+//   RA  [2B][h][w] float4 / RB [2B][h][w] float : polynomial expansion coefficients (y, x, yy, xx | xy)
 //   M                     structure-tensor entries: shared memory only (fused iteration kernel)
 //   flow[B][h][w][2]      f32  (dx, dy), ping-pong between levels
 #include <math.h>
@@ -56,21 +56,29 @@ k4_pyr_level(const uint8_t* __restrict__ gray0, const uint8_t* __restrict__ gray
   uint8_t* src = py_smem;                                         // [sh][sw_p] uint8
   float* hs = reinterpret_cast<float*>(py_smem + (((size_t)sh * sw_p + 15) & ~(size_t)15));   // [sh][2*PY_TX] f32
   const int tid = threadIdx.x;
-  for (int i = tid; i < sh * sw; i += 256) {
-    const int ty = i / sw, tx = i - ty * sw;
-    src[ty * sw_p + tx] = img[(size_t)reflect101(y_lo + ty, H) * W + reflect101(x_lo + tx, W)];
+  const int wrp = tid >> 5, lane = tid & 31;
+  for (int ty = wrp; ty < sh; ty += 8) {                           // one warp per source row
+    const uint8_t* grow = img + (size_t)reflect101(y_lo + ty, H) * W;
+    for (int tx = lane; tx < sw; tx += 32) src[ty * sw_p + tx] = grow[reflect101(x_lo + tx, W)];
   }
   __syncthreads();
   // horizontal pass at the needed columns: column slot 2j / 2j+1 = left / right tap of output xo0 + j
-  for (int i = tid; i < sh * 2 * PY_TX; i += 256) {
-    const int ty = i / (2 * PY_TX), slot = i - ty * (2 * PY_TX);
+  int xc2[2];
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    const int slot = lane + 32 * u;
     const int xo = min(xo0 + (slot >> 1), w - 1);
     lin_split(xo, sx, W, same, i0, i1, a);
-    const int xc = ((slot & 1) ? i1 : i0) - r - x_lo;              // window start inside the tile
-    const uint8_t* row = src + ty * sw_p + xc;
-    float acc = 0.f;
-    for (int k = 0; k < taps.ksize; ++k) acc += taps.t[k] * (float)row[k];
-    hs[i] = acc;
+    xc2[u] = ((slot & 1) ? i1 : i0) - r - x_lo;                    // window start inside the tile
+  }
+  for (int ty = wrp; ty < sh; ty += 8) {
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const uint8_t* row = src + ty * sw_p + xc2[u];
+      float acc = 0.f;
+      for (int k = 0; k < taps.ksize; ++k) acc += taps.t[k] * (float)row[k];
+      hs[ty * (2 * PY_TX) + lane + 32 * u] = acc;
+    }
   }
   __syncthreads();
   const int tx = tid & (PY_TX - 1), ty = tid / PY_TX;
@@ -91,66 +99,96 @@ k4_pyr_level(const uint8_t* __restrict__ gray0, const uint8_t* __restrict__ gray
   }
 }
 
-// ---- (c) polynomial expansion: I [h][w] -> R planes.  Tile 32 x 16, halo 5, smem staged.
-constexpr int PE_TW = 32, PE_TH = 16, PE_N = 5;
+// ---- (c) polynomial expansion: I -> R.  Tile 64 x 16 outputs, halo 5; each thread produces 4 consecutive
+// values per pass from a 14-value register window (3x fewer shared-memory loads than one value per thread).
+// R layout: RA [img][h][w] float4 = (y, x, yy, xx) coefficients, RB [img][h][w] float = xy coefficient.
+// kFromGray (finest level): I = GaussianBlur(gray, 3x3, taps .25 .5 .25, REFLECT_101) is computed on the fly
+// from the uint8 image, so the full-resolution f32 image never exists in HBM.
+constexpr int PE_TW = 64, PE_TH = 16, PE_N = 5, PE_LW = PE_TW + 2 * PE_N, PE_LH = PE_TH + 2 * PE_N;   // 74, 26
+template <bool kFromGray>
 __global__ void __launch_bounds__(256)
-k4_polyexp(const float* __restrict__ I, int h, int w, PolyConsts pc, float* __restrict__ R) {
-  __shared__ float tile[PE_TH + 2 * PE_N][PE_TW + 2 * PE_N + 1];
-  __shared__ float v0[PE_TH][PE_TW + 2 * PE_N + 1], v1[PE_TH][PE_TW + 2 * PE_N + 1], v2[PE_TH][PE_TW + 2 * PE_N + 1];
-  const int x0 = blockIdx.x * PE_TW, y0 = blockIdx.y * PE_TH;
-  const float* img = I + (size_t)blockIdx.z * h * w;
-  const int tid = threadIdx.x;
-  for (int i = tid; i < (PE_TH + 2 * PE_N) * (PE_TW + 2 * PE_N); i += 256) {
-    const int ty = i / (PE_TW + 2 * PE_N), tx = i % (PE_TW + 2 * PE_N);
-    const int gy = min(max(y0 + ty - PE_N, 0), h - 1), gx = min(max(x0 + tx - PE_N, 0), w - 1);
-    tile[ty][tx] = img[(size_t)gy * w + gx];
+k4_polyexp(const float* __restrict__ I, const uint8_t* __restrict__ gray0, const uint8_t* __restrict__ gray1, int B, int h, int w,
+           PolyConsts pc, float4* __restrict__ RA, float* __restrict__ RB) {
+  __shared__ float tile[PE_LH][PE_LW + 1];
+  __shared__ float v0[PE_TH][PE_LW + 1], v1[PE_TH][PE_LW + 1], v2[PE_TH][PE_LW + 1];
+  __shared__ float hrow[kFromGray ? PE_LH + 2 : 1][kFromGray ? PE_LW + 3 : 1];
+  const int x0 = blockIdx.x * PE_TW, y0 = blockIdx.y * PE_TH, z = blockIdx.z;
+  const int tid = threadIdx.x, wrp = tid >> 5, lane = tid & 31;
+  if (kFromGray) {
+    const uint8_t* g = (z < B ? gray0 + (size_t)z * h * w : gray1 + (size_t)(z - B) * h * w);
+    // row-filtered gray at raw coordinates (y0-6+ty, x0-5+tx): rows 0..27, cols 0..73
+    for (int ty = wrp; ty < PE_LH + 2; ty += 8) {
+      const uint8_t* grow = g + (size_t)reflect101(min(max(y0 - 6 + ty, -1), h), h) * w;
+      for (int tx = lane; tx < PE_LW; tx += 32) {
+        const int cx = min(max(x0 - PE_N + tx, 0), w - 1);            // I is replicated outside the image
+        const float a = (float)grow[reflect101(cx - 1, w)], b = (float)grow[cx], c = (float)grow[reflect101(cx + 1, w)];
+        hrow[ty][tx] = 0.25f * a + 0.5f * b + 0.25f * c;
+      }
+    }
+    __syncthreads();
+    for (int ty = wrp; ty < PE_LH; ty += 8) {
+      const int cy = min(max(y0 - PE_N + ty, 0), h - 1);
+      const int r = cy - (y0 - 6);                                      // hrow row of image row cy
+      for (int tx = lane; tx < PE_LW; tx += 32) tile[ty][tx] = 0.25f * hrow[r - 1][tx] + 0.5f * hrow[r][tx] + 0.25f * hrow[r + 1][tx];
+    }
+  } else {
+    const float* img = I + (size_t)z * h * w;
+    for (int ty = wrp; ty < PE_LH; ty += 8) {
+      const float* irow = img + (size_t)min(max(y0 + ty - PE_N, 0), h - 1) * w;
+      for (int tx = lane; tx < PE_LW; tx += 32) tile[ty][tx] = irow[min(max(x0 + tx - PE_N, 0), w - 1)];
+    }
   }
   __syncthreads();
-  // vertical pass (f32): rows clamped -> the tile already holds clamped rows.  NB: row clamping of the
-  // *source* index equals OpenCV's max(y-k,0)/min(y+k,h-1) because tile rows were clamped on load.
-  for (int i = tid; i < PE_TH * (PE_TW + 2 * PE_N); i += 256) {
-    const int ty = i / (PE_TW + 2 * PE_N), tx = i % (PE_TW + 2 * PE_N);
-    const int c = ty + PE_N;
-    float r0 = tile[c][tx] * pc.g[0], r1 = 0.f, r2 = 0.f;
+  // vertical pass: task = (column, group of 4 rows); 74 * 4 = 296 tasks
+  for (int task = tid; task < PE_LW * (PE_TH / 4); task += 256) {
+    const int tx = task % PE_LW, rg = task / PE_LW;
+    float win[14];
 #pragma unroll
-    for (int k = 1; k <= PE_N; ++k) {
-      const float up = tile[c - k][tx], dn = tile[c + k][tx];
-      const float p = up + dn;
-      r0 = r0 + pc.g[k] * p;
-      r1 = r1 + pc.xg[k] * (dn - up);
-      r2 = r2 + pc.xxg[k] * p;
+    for (int i = 0; i < 14; ++i) win[i] = tile[rg * 4 + i][tx];
+#pragma unroll
+    for (int o = 0; o < 4; ++o) {
+      float r0 = win[o + 5] * pc.g[0], r1 = 0.f, r2 = 0.f;
+#pragma unroll
+      for (int k = 1; k <= PE_N; ++k) {
+        const float up = win[o + 5 - k], dn = win[o + 5 + k], p = up + dn;
+        r0 = r0 + pc.g[k] * p;
+        r1 = r1 + pc.xg[k] * (dn - up);
+        r2 = r2 + pc.xxg[k] * p;
+      }
+      v0[rg * 4 + o][tx] = r0; v1[rg * 4 + o][tx] = r1; v2[rg * 4 + o][tx] = r2;
     }
-    v0[ty][tx] = r0; v1[ty][tx] = r1; v2[ty][tx] = r2;
   }
   __syncthreads();
-  // horizontal pass.  OpenCV accumulates this pass in f64; f32 changes the flow by < 1e-5 px (measured, see
-  // DESIGN.md) and avoids the quarter-rate f32->f64 conversions.  Columns beyond the image replicate the edge
-  // column of the *vertical* result - which is what the clamped tile load produced.
-  const size_t plane = (size_t)h * w;
-  float* Rb = R + (size_t)blockIdx.z * 5 * plane;
-  for (int i = tid; i < PE_TH * PE_TW; i += 256) {
-    const int ty = i / PE_TW, tx = i % PE_TW;
-    const int gx = x0 + tx, gy = y0 + ty;
-    if (gx >= w || gy >= h) continue;
-    const int c = tx + PE_N;
-    float b1 = v0[ty][c] * pc.g[0], b2 = 0.f, b3 = v1[ty][c] * pc.g[0], b4 = 0.f, b5 = v2[ty][c] * pc.g[0], b6 = 0.f;
+  // horizontal pass (f32; OpenCV uses f64 accumulators here - the flow changes by < 1e-5 px):
+  // task = (row, group of 4 columns) = 16 * 16 = 256
+  {
+    const int ty = tid >> 4, cg = tid & 15;
+    const int gy = y0 + ty;
+    float a0[14], a1[14], a2[14];
 #pragma unroll
-    for (int k = 1; k <= PE_N; ++k) {
-      const float p0 = v0[ty][c + k], m0 = v0[ty][c - k], p1 = v1[ty][c + k], m1 = v1[ty][c - k], p2 = v2[ty][c + k], m2 = v2[ty][c - k];
-      const float tg = p0 + m0;
-      b1 += tg * pc.g[k];
-      b4 += tg * pc.xxg[k];
-      b2 += (p0 - m0) * pc.xg[k];
-      b3 += (p1 + m1) * pc.g[k];
-      b6 += (p1 - m1) * pc.xg[k];
-      b5 += (p2 + m2) * pc.g[k];
+    for (int i = 0; i < 14; ++i) { a0[i] = v0[ty][cg * 4 + i]; a1[i] = v1[ty][cg * 4 + i]; a2[i] = v2[ty][cg * 4 + i]; }
+    const size_t plane = (size_t)h * w;
+#pragma unroll
+    for (int o = 0; o < 4; ++o) {
+      const int gx = x0 + cg * 4 + o;
+      const int c = o + 5;
+      float b1 = a0[c] * pc.g[0], b2 = 0.f, b3 = a1[c] * pc.g[0], b4 = 0.f, b5 = a2[c] * pc.g[0], b6 = 0.f;
+#pragma unroll
+      for (int k = 1; k <= PE_N; ++k) {
+        const float tg = a0[c + k] + a0[c - k];
+        b1 += tg * pc.g[k];
+        b4 += tg * pc.xxg[k];
+        b2 += (a0[c + k] - a0[c - k]) * pc.xg[k];
+        b3 += (a1[c + k] + a1[c - k]) * pc.g[k];
+        b6 += (a1[c + k] - a1[c - k]) * pc.xg[k];
+        b5 += (a2[c + k] + a2[c - k]) * pc.g[k];
+      }
+      if (gx < w && gy < h) {
+        const size_t oo = (size_t)z * plane + (size_t)gy * w + gx;
+        RA[oo] = make_float4(b3 * pc.ig11, b2 * pc.ig11, b1 * pc.ig03 + b5 * pc.ig33, b1 * pc.ig03 + b4 * pc.ig33);
+        RB[oo] = b6 * pc.ig55;
+      }
     }
-    const size_t o = (size_t)gy * w + gx;
-    Rb[o] = b3 * pc.ig11;
-    Rb[plane + o] = b2 * pc.ig11;
-    Rb[2 * plane + o] = b1 * pc.ig03 + b5 * pc.ig33;
-    Rb[3 * plane + o] = b1 * pc.ig03 + b4 * pc.ig33;
-    Rb[4 * plane + o] = b6 * pc.ig55;
   }
 }
 
@@ -164,89 +202,95 @@ __device__ __forceinline__ float border_w(int i, int n) {
   return s;
 }
 
-constexpr int BX_T = 32, BX_M = 7, BX_IN = BX_T + 2 * BX_M, BX_LD = BX_IN + 1;     // 46, 47
-constexpr int BX_SMEM = (5 * BX_IN * BX_LD + 5 * BX_T * BX_LD) * 4;
+constexpr int BX_TX = 64, BX_TY = 32, BX_M = 7, BX_W = BX_TX + 2 * BX_M, BX_H = BX_TY + 2 * BX_M, BX_LD = BX_W + 1;   // 78, 46, 79
+constexpr int BX_SMEM = 5 * BX_H * BX_LD * 4;
 __global__ void __launch_bounds__(256)
-k4_flow_iter(const float* __restrict__ R0, const float* __restrict__ R1, const float* __restrict__ flow_in, int h, int w,
-             float* __restrict__ flow_out) {
-  extern __shared__ float bx_smem[];
-  float* Ms = bx_smem;                               // [5][46][47]
-  float* Vs = bx_smem + 5 * BX_IN * BX_LD;           // [5][32][47]
-  const int x0 = blockIdx.x * BX_T, y0 = blockIdx.y * BX_T;
-  const size_t plane = (size_t)h * w;
-  const float* r0 = R0 + (size_t)blockIdx.z * 5 * plane;
-  const float* r1 = R1 + (size_t)blockIdx.z * 5 * plane;
-  const float2* fin = reinterpret_cast<const float2*>(flow_in) + (size_t)blockIdx.z * plane;
-  const int tid = threadIdx.x;
-  // phase A: structure-tensor entries at the (replicate-clamped) halo pixels
-  for (int i = tid; i < BX_IN * BX_IN; i += 256) {
-    const int ty = i / BX_IN, tx = i - ty * BX_IN;
-    const int x = min(max(x0 + tx - BX_M, 0), w - 1), y = min(max(y0 + ty - BX_M, 0), h - 1);
-    const size_t o = (size_t)y * w + x;
-    const float2 d = fin[o];
-    const float dx = d.x, dy = d.y;
-    float fx = (float)x + dx, fy = (float)y + dy;
-    const int x1 = (int)floorf(fx), y1 = (int)floorf(fy);
-    fx -= (float)x1; fy -= (float)y1;
-    float r2, r3, r4, r5, r6;
-    const float a4 = r0[2 * plane + o], a5 = r0[3 * plane + o], a6 = r0[4 * plane + o];
-    if ((unsigned)x1 < (unsigned)(w - 1) && (unsigned)y1 < (unsigned)(h - 1)) {
-      const float a00 = (1.f - fx) * (1.f - fy), a01 = fx * (1.f - fy), a10 = (1.f - fx) * fy, a11 = fx * fy;
-      const size_t q = (size_t)y1 * w + x1;
-#define BIL(c) (a00 * r1[(c) * plane + q] + a01 * r1[(c) * plane + q + 1] + a10 * r1[(c) * plane + q + w] + a11 * r1[(c) * plane + q + w + 1])
-      r2 = BIL(0); r3 = BIL(1); r4 = BIL(2); r5 = BIL(3); r6 = BIL(4);
-#undef BIL
-      r4 = (a4 + r4) * 0.5f; r5 = (a5 + r5) * 0.5f; r6 = (a6 + r6) * 0.25f;
-    } else {
-      r2 = r3 = 0.f; r4 = a4; r5 = a5; r6 = a6 * 0.5f;
+k4_flow_iter(const float4* __restrict__ RA0, const float* __restrict__ RB0, const float4* __restrict__ RA1,
+             const float* __restrict__ RB1, const float* __restrict__ flow_in, int h, int w, float* __restrict__ flow_out) {
+  extern __shared__ float Ms[];                      // [5][46][79]; rows 0..31 become the vertical sums in place
+  const int x0 = blockIdx.x * BX_TX, y0 = blockIdx.y * BX_TY;
+  const size_t plane = (size_t)h * w, zo = (size_t)blockIdx.z * plane;
+  const float2* fin = reinterpret_cast<const float2*>(flow_in) + zo;
+  const int tid = threadIdx.x, wrp = tid >> 5, lane = tid & 31;
+  // phase A: structure-tensor entries at the (replicate-clamped) halo pixels; one warp per halo row
+  for (int ty = wrp; ty < BX_H; ty += 8) {
+    const int y = min(max(y0 + ty - BX_M, 0), h - 1);
+    for (int tx = lane; tx < BX_W; tx += 32) {
+      const int x = min(max(x0 + tx - BX_M, 0), w - 1);
+      const size_t o = (size_t)y * w + x;
+      const float2 d = fin[o];
+      const float4 c0 = RA0[zo + o];
+      const float c0xy = RB0[zo + o];
+      const float dx = d.x, dy = d.y;
+      float fx = (float)x + dx, fy = (float)y + dy;
+      const int x1 = (int)floorf(fx), y1 = (int)floorf(fy);
+      fx -= (float)x1; fy -= (float)y1;
+      float r2, r3, r4, r5, r6;
+      if ((unsigned)x1 < (unsigned)(w - 1) && (unsigned)y1 < (unsigned)(h - 1)) {
+        const float a00 = (1.f - fx) * (1.f - fy), a01 = fx * (1.f - fy), a10 = (1.f - fx) * fy, a11 = fx * fy;
+        const size_t q = zo + (size_t)y1 * w + x1;
+        const float4 p00 = RA1[q], p01 = RA1[q + 1], p10 = RA1[q + w], p11 = RA1[q + w + 1];
+        const float s00 = RB1[q], s01 = RB1[q + 1], s10 = RB1[q + w], s11 = RB1[q + w + 1];
+        r2 = a00 * p00.x + a01 * p01.x + a10 * p10.x + a11 * p11.x;
+        r3 = a00 * p00.y + a01 * p01.y + a10 * p10.y + a11 * p11.y;
+        r4 = a00 * p00.z + a01 * p01.z + a10 * p10.z + a11 * p11.z;
+        r5 = a00 * p00.w + a01 * p01.w + a10 * p10.w + a11 * p11.w;
+        r6 = a00 * s00 + a01 * s01 + a10 * s10 + a11 * s11;
+        r4 = (c0.z + r4) * 0.5f; r5 = (c0.w + r5) * 0.5f; r6 = (c0xy + r6) * 0.25f;
+      } else {
+        r2 = r3 = 0.f; r4 = c0.z; r5 = c0.w; r6 = c0xy * 0.5f;
+      }
+      r2 = (c0.x - r2) * 0.5f;
+      r3 = (c0.y - r3) * 0.5f;
+      r2 += r4 * dy + r6 * dx;
+      r3 += r6 * dy + r5 * dx;
+      if ((unsigned)(x - 5) >= (unsigned)(w - 10) || (unsigned)(y - 5) >= (unsigned)(h - 10)) {
+        const float s = border_w(y, h) * border_w(x, w);
+        r2 *= s; r3 *= s; r4 *= s; r5 *= s; r6 *= s;
+      }
+      float* m = Ms + ty * BX_LD + tx;
+      m[0] = r4 * r4 + r6 * r6;
+      m[BX_H * BX_LD] = (r4 + r5) * r6;
+      m[2 * BX_H * BX_LD] = r5 * r5 + r6 * r6;
+      m[3 * BX_H * BX_LD] = r4 * r2 + r6 * r3;
+      m[4 * BX_H * BX_LD] = r6 * r2 + r5 * r3;
     }
-    r2 = (r0[o] - r2) * 0.5f;
-    r3 = (r0[plane + o] - r3) * 0.5f;
-    r2 += r4 * dy + r6 * dx;
-    r3 += r6 * dy + r5 * dx;
-    if ((unsigned)(x - 5) >= (unsigned)(w - 10) || (unsigned)(y - 5) >= (unsigned)(h - 10)) {
-      const float s = border_w(y, h) * border_w(x, w);
-      r2 *= s; r3 *= s; r4 *= s; r5 *= s; r6 *= s;
-    }
-    float* m = Ms + ty * BX_LD + tx;
-    m[0] = r4 * r4 + r6 * r6;
-    m[BX_IN * BX_LD] = (r4 + r5) * r6;
-    m[2 * BX_IN * BX_LD] = r5 * r5 + r6 * r6;
-    m[3 * BX_IN * BX_LD] = r4 * r2 + r6 * r3;
-    m[4 * BX_IN * BX_LD] = r6 * r2 + r5 * r3;
   }
   __syncthreads();
-  // phase B: vertical sliding sums (f32; the walk is only 32 rows long, error ~ that of a direct 15-tap sum)
-  if (tid < 5 * BX_IN) {
-    const int c = tid / BX_IN, j = tid - c * BX_IN;
-    const float* col = Ms + (size_t)c * BX_IN * BX_LD + j;
-    float* dst = Vs + (size_t)c * BX_T * BX_LD + j;
+  // phase B: vertical sliding sums, in place (f32; the walk is 32 rows, error ~ a direct 15-tap sum).
+  // The sum for output row r is written over input row r one step late, after that row's last use.
+  for (int task = tid; task < 5 * BX_W; task += 256) {
+    const int c = task / BX_W, j = task - c * BX_W;
+    float* col = Ms + (size_t)c * BX_H * BX_LD + j;
     float s = 0.f;
 #pragma unroll
     for (int i = 0; i < 15; ++i) s += col[i * BX_LD];
-    dst[0] = s;
-    for (int rr = 1; rr < BX_T; ++rr) {
-      s += col[(rr + 14) * BX_LD] - col[(rr - 1) * BX_LD];
-      dst[rr * BX_LD] = s;
+    float prev = s;
+    for (int rr = 1; rr < BX_TY; ++rr) {
+      const float add = col[(rr + 14) * BX_LD], sub = col[(rr - 1) * BX_LD];
+      col[(rr - 1) * BX_LD] = prev;
+      s += add - sub;
+      prev = s;
     }
+    col[(BX_TY - 1) * BX_LD] = prev;
   }
   __syncthreads();
-  // phase C: horizontal sums over 4-column segments + solve (f64, as OpenCV): task = (row, segment)
+  // phase C: horizontal sums over 8-column segments + solve (f64 solve, as OpenCV): warp = segment, lane = row
   {
-    const int rr = tid >> 3, seg = tid & 7;
+    const int rr = lane, seg = wrp;
     const int gy = y0 + rr;
     float g[5];
 #pragma unroll
     for (int c = 0; c < 5; ++c) {
-      const float* row = Vs + ((size_t)c * BX_T + rr) * BX_LD + seg * 4;
+      const float* row = Ms + ((size_t)c * BX_H + rr) * BX_LD + seg * 8;
       float s = 0.f;
 #pragma unroll
       for (int i = 0; i < 15; ++i) s += row[i];
       g[c] = s;
     }
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int gx = x0 + seg * 4 + k;
+    for (int k = 0; k < 8; ++k) {
+      const int gx = x0 + seg * 8 + k;
       if (gx < w && gy < h) {
         const double sc = 1.0 / 225.0;
         const double g11 = g[0] * sc, g12 = g[1] * sc, g22 = g[2] * sc, h1 = g[3] * sc, h2 = g[4] * sc;
@@ -254,12 +298,14 @@ k4_flow_iter(const float* __restrict__ R0, const float* __restrict__ R1, const f
         float2 f;
         f.x = (float)((g11 * h2 - g12 * h1) * idet);
         f.y = (float)((g22 * h1 - g12 * h2) * idet);
-        reinterpret_cast<float2*>(flow_out)[(size_t)blockIdx.z * plane + (size_t)gy * w + gx] = f;
+        reinterpret_cast<float2*>(flow_out)[zo + (size_t)gy * w + gx] = f;
       }
+      if (k < 7) {
 #pragma unroll
-      for (int c = 0; c < 5; ++c) {
-        const float* row = Vs + ((size_t)c * BX_T + rr) * BX_LD + seg * 4 + k;
-        g[c] += row[15] - row[0];
+        for (int c = 0; c < 5; ++c) {
+          const float* row = Ms + ((size_t)c * BX_H + rr) * BX_LD + seg * 8 + k;
+          g[c] += row[15] - row[0];
+        }
       }
     }
   }
@@ -345,13 +391,15 @@ __device__ __forceinline__ uchar3 flow_colour(float dx, float dy, double nscale,
   int sector = (int)floorf(hh);
   const float f = __fsub_rn(hh, (float)sector);
   sector %= 6;
-  float tab[4];
-  tab[0] = v;
-  tab[1] = __fmul_rn(v, __fsub_rn(1.f, s));
-  tab[2] = __fmul_rn(v, __fsub_rn(1.f, __fmul_rn(s, f)));
-  tab[3] = __fmul_rn(v, __fsub_rn(1.f, __fmul_rn(s, __fsub_rn(1.f, f))));
-  const int ib[6] = {1, 1, 3, 0, 0, 2}, ig[6] = {3, 0, 0, 2, 1, 1}, ir[6] = {0, 2, 1, 1, 3, 0};
-  const float b = __fmul_rn(tab[ib[sector]], 255.f), g = __fmul_rn(tab[ig[sector]], 255.f), r = __fmul_rn(tab[ir[sector]], 255.f);
+  const float t0 = v;
+  const float t1 = __fmul_rn(v, __fsub_rn(1.f, s));
+  const float t2 = __fmul_rn(v, __fsub_rn(1.f, __fmul_rn(s, f)));
+  const float t3 = __fmul_rn(v, __fsub_rn(1.f, __fmul_rn(s, __fsub_rn(1.f, f))));
+  // sector -> (b, g, r) table {1,3,0},{1,0,2},{3,0,1},{0,2,1},{0,1,3},{2,1,0} as selects (no local memory)
+  const float bsel = sector < 2 ? t1 : (sector == 2 ? t3 : (sector < 5 ? t0 : t2));
+  const float gsel = sector == 0 ? t3 : (sector < 3 ? t0 : (sector == 3 ? t2 : t1));
+  const float rsel = sector == 0 ? t0 : (sector == 1 ? t2 : (sector < 4 ? t1 : (sector == 4 ? t3 : t0)));
+  const float b = __fmul_rn(bsel, 255.f), g = __fmul_rn(gsel, 255.f), r = __fmul_rn(rsel, 255.f);
   return make_uchar3((unsigned char)fminf(fmaxf(b, 0.f), 255.f), (unsigned char)fminf(fmaxf(g, 0.f), 255.f),
                      (unsigned char)fminf(fmaxf(r, 0.f), 255.f));
 }
@@ -495,15 +543,19 @@ extern "C" int b200vqa_farneback(b200vqa_t* h, const uint8_t* gray0, const uint8
   CtxScope scope(h);
   cudaStream_t st = as_stream(stream);
   const size_t P = (size_t)H * W;
-  // workspace (float): I [2][B][P] | R [2][B][5][P] | flowA, flowB [B][P][2]
+  // workspace (float units): RA [2B][P] float4 | RB [2B][P] | I [2B][P/4] (levels >= 1 only) | flowA, flowB [B][P][2]
   const std::vector<Level> plan = pyramid_plan(H, W);
-  const size_t floats = (size_t)B * P * (2 + 10 + 4);
+  size_t Pq = 16;
+  for (size_t li = 0; li + 1 < plan.size(); ++li) Pq = std::max(Pq, (size_t)plan[li].h * plan[li].w);
+  if (plan.size() == 1) Pq = P;
+  const size_t floats = (size_t)B * (P * (8 + 2 + 4) + Pq * 2) + 64;
   int rc = h->ws_flow.reserve(floats * sizeof(float));
   if (rc) return rc;
-  float* I = static_cast<float*>(h->ws_flow.ptr);
-  float* R = I + 2 * (size_t)B * P;
-  float* flowA = R + 10 * (size_t)B * P;
+  float4* RA = static_cast<float4*>(h->ws_flow.ptr);
+  float* RB = reinterpret_cast<float*>(RA + 2 * (size_t)B * P);
+  float* flowA = RB + 2 * (size_t)B * P;
   float* flowB = flowA + 2 * (size_t)B * P;
+  float* I = flowB + 2 * (size_t)B * P;
   static const PolyConsts pc = poly_consts();
   static bool attr_done = false;
   if (!attr_done) {
@@ -518,8 +570,13 @@ extern "C" int b200vqa_farneback(b200vqa_t* h, const uint8_t* gray0, const uint8
     const bool last = li + 1 == plan.size();
     const Taps taps = gaussian_taps(L.ksize, L.sigma);
     const size_t lp = (size_t)L.h * L.w;
-    float* R0 = R; float* R1 = R + (size_t)B * 5 * lp;
-    {
+    const float4* RA0 = RA; const float4* RA1 = RA + (size_t)B * lp;
+    const float* RB0 = RB; const float* RB1 = RB + (size_t)B * lp;
+    if (L.h == H && L.w == W) {
+      // finest level: 3x3 blur fused into the expansion (no f32 image in HBM)
+      k4_polyexp<true><<<dim3(cdiv(L.w, PE_TW), cdiv(L.h, PE_TH), 2 * B), 256, 0, st>>>(nullptr, gray0, gray1, B, L.h, L.w, pc, RA, RB);
+      VQA_LAUNCH_CHECK();
+    } else {
       const double sx = (double)W / L.w, sy = (double)H / L.h;
       // shared-memory window: uint8 source tile + f32 horizontally blurred columns
       const int sw = (int)(PY_TX * sx) + L.ksize + 4, sh = (int)(PY_TY * sy) + L.ksize + 4;
@@ -527,8 +584,8 @@ extern "C" int b200vqa_farneback(b200vqa_t* h, const uint8_t* gray0, const uint8
       if (smem > 100 * 1024) return B200VQA_EINVAL;
       k4_pyr_level<<<dim3(cdiv(L.w, PY_TX), cdiv(L.h, PY_TY), 2 * B), 256, smem, st>>>(gray0, gray1, B, H, W, taps, L.h, L.w, sx, sy, I);
       VQA_LAUNCH_CHECK();
-      // I holds [2B][h][w]; R0 = expansion of images 0..B-1, R1 of B..2B-1 (contiguous)
-      k4_polyexp<<<dim3(cdiv(L.w, PE_TW), cdiv(L.h, PE_TH), 2 * B), 256, 0, st>>>(I, L.h, L.w, pc, R0);
+      // I holds [2B][h][w]; expansion of images 0..B-1 then B..2B-1 (contiguous)
+      k4_polyexp<false><<<dim3(cdiv(L.w, PE_TW), cdiv(L.h, PE_TH), 2 * B), 256, 0, st>>>(I, nullptr, nullptr, B, L.h, L.w, pc, RA, RB);
       VQA_LAUNCH_CHECK();
     }
     float* fin = flowA;
@@ -540,11 +597,11 @@ extern "C" int b200vqa_farneback(b200vqa_t* h, const uint8_t* gray0, const uint8
       k4_flow_upsample<<<dim3(cdiv(L.w, 256), L.h, B), 256, 0, st>>>(prev, ph, pw, L.h, L.w, (double)pw / L.w, (double)ph / L.h, fin);
       VQA_LAUNCH_CHECK();
     }
-    const dim3 gbox(cdiv(L.w, BX_T), cdiv(L.h, BX_T), B);
+    const dim3 gbox(cdiv(L.w, BX_TX), cdiv(L.h, BX_TY), B);
     float* fout = nullptr;
     for (int it = 0; it < 3; ++it) {
       fout = (last && it == 2) ? flow : (fin == flowA ? flowB : flowA);
-      k4_flow_iter<<<gbox, 256, BX_SMEM, st>>>(R0, R1, fin, L.h, L.w, fout);
+      k4_flow_iter<<<gbox, 256, BX_SMEM, st>>>(RA0, RB0, RA1, RB1, fin, L.h, L.w, fout);
       VQA_LAUNCH_CHECK();
       fin = fout;
     }

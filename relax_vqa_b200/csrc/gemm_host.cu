@@ -42,7 +42,9 @@ int make_tmap_f16(CUtensorMap* map, const void* base, int rank, const uint64_t* 
   return B200VQA_OK;
 }
 
-int launch_gemm(const CUtensorMap& map_a, const CUtensorMap& map_b, const GemmParams& p, int sm_count, cudaStream_t st) {
+int launch_gemm(const CUtensorMap& map_a, const CUtensorMap& map_b, const GemmParams& p, int sm_count, cudaStream_t st,
+                const CUtensorMap* map_eye, const CUtensorMap* map_idt) {
+  if (p.idt_blocks && (!map_eye || !map_idt || p.idt_blocks != 2)) return B200VQA_EINVAL;
   if (p.block_n % 16 || p.block_n < 16 || p.block_n > 256 || p.stages < 2 || p.stages > GEMM_MAX_STAGES) return B200VQA_EINVAL;
   const size_t smem = gemm_smem_bytes(p.block_n, p.stages);
   if (smem > 227 * 1024) return B200VQA_EINVAL;
@@ -61,12 +63,12 @@ int launch_gemm(const CUtensorMap& map_a, const CUtensorMap& map_b, const GemmPa
     else { VQA_CUDA(cudaEventCreate(&ev.first)); VQA_CUDA(cudaEventCreate(&ev.second)); }
     VQA_CUDA(cudaEventRecord(ev.first, st));
   }
-  gemm_tcgen05_kernel<<<grid, GEMM_THREADS, smem, st>>>(map_a, map_b, p);
+  gemm_tcgen05_kernel<<<grid, GEMM_THREADS, smem, st>>>(map_a, map_b, map_eye ? *map_eye : map_a, map_idt ? *map_idt : map_b, p);
   if (prof) {
     VQA_CUDA(cudaEventRecord(ev.second, st));
     ctx->prof_events.push_back(ev);
     // algorithmic FLOPs of the un-padded problem
-    const double kdepth = (double)p.taps_r * p.taps_s * p.k_blocks_per_tap * GEMM_BK;
+    const double kdepth = (double)p.taps_r * p.taps_s * p.k_blocks_per_tap * GEMM_BK;   // identity K-blocks are not counted
     if (p.epi == EPI_ROW) ctx->prof_flops += 2.0 * p.M * p.N * kdepth;
     else ctx->prof_flops += 2.0 * p.M * ((double)p.Nimg * p.Hout * p.Wout) * (p.b_is_conv ? kdepth : 147.0);
   }

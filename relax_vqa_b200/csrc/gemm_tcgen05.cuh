@@ -18,7 +18,10 @@
 //   EPI_ROW  (linear layers; A rows = tokens, B rows = output features):
 //       out[m][n] = act(acc + bias[n]) (+ residual[m][n]), fp16 or fp32 row-major
 //   EPI_CONV (convolutions; A rows = output channels, B rows = output pixels):
-//       v = acc*scale[c] + shift[c] (+ identity[pix][c]); ReLU; out[pix][c] fp16 NHWC;
+//       v = acc*scale[c] + shift[c]; ReLU; out[pix][c] fp16 NHWC.  The bottleneck's residual identity is
+//       added by the tensor core itself: two extra K-blocks whose A tile is a one-hot (identity) matrix
+//       and whose B tile is the identity tensor fetched by TMA (BN scale is folded into the weights, so
+//       acc = scale*conv + identity exactly); the epilogue therefore issues no global loads.
 //       optional per-(image, tile, channel) partial sums of v (or of the raw acc) for the
 //       fused layer-stack global average pooling - written, not atomically added, so the
 //       reduction order is fixed and results are bit-reproducible.
@@ -63,7 +66,7 @@ struct GemmParams {
   void* out;
   const float* scale;            // EPI_CONV: [Cout]
   const float* shift;            // EPI_CONV: [Cout]
-  const __half* identity;        // EPI_CONV: NHWC fp16 [Nimg][Hout][Wout][Cout] or null
+  int idt_blocks;                // EPI_CONV: 0, or 2 = residual identity added by the tensor core (see kernel)
   float* gap_partial;            // EPI_CONV: [Nimg][tiles_y * GEMM_EPI_GROUPS][Cout] or null
   int gap_raw;                   // pool the raw accumulator (conv1 hook is pre-BN)
 };
@@ -157,6 +160,7 @@ __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + e
 #ifdef B200VQA_GEMM_KERNEL_TU      // defined by gemm_host.cu only (one definition per library)
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                    const __grid_constant__ CUtensorMap map_eye, const __grid_constant__ CUtensorMap map_idt,
                     const GemmParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -171,7 +175,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_tiles = p.m_tiles * p.n_tiles;
-  const int k_blocks = p.taps_r * p.taps_s * p.k_blocks_per_tap;
+  const int conv_blocks = p.taps_r * p.taps_s * p.k_blocks_per_tap;
+  const int k_blocks = conv_blocks + p.idt_blocks;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
@@ -209,6 +214,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
           uint8_t* sa = smem + (size_t)stage * stage_bytes;
           uint8_t* sb = sa + a_bytes;
           mbar_expect_tx(&full_bar[stage], stage_bytes);
+          if (kb >= conv_blocks) {
+            // residual identity: D[c][pix] += sum_k onehot[c][k] * identity[pix][mt*128 + 64*j + k]
+            const int j = kb - conv_blocks;
+            tma_load_2d(&map_eye, &full_bar[stage], sa, j * GEMM_BK, 0);
+            tma_load_4d(&map_idt, &full_bar[stage], sb, mt * GEMM_BM + j * GEMM_BK, 0, by + p.conv_pad, bn);
+            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            continue;
+          }
           tma_load_2d(&map_a, &full_bar[stage], sa, kb * GEMM_BK, mt * GEMM_BM);
           if (p.b_is_conv) {
             const int tap = kb / p.k_blocks_per_tap, cb = kb % p.k_blocks_per_tap;
@@ -336,60 +349,86 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         // EPI_CONV: this thread owns output channel c; columns are output pixels of the box.
         // The two warps of a quadrant split the pixel columns into contiguous halves (16-px chunks).
         const int c = mt * GEMM_BM + row;
-        const bool c_ok = c < p.M;
-        const float sc = c_ok ? p.scale[c] : 0.f, sh = c_ok ? p.shift[c] : 0.f;
         const int ty = nt % p.tiles_y, tg = nt / p.tiles_y;
-        const int per_img = p.tw * p.th;
-        const int nchunks = p.block_n >> 4;
-        const int half = (nchunks + GEMM_EPI_GROUPS - 1) / GEMM_EPI_GROUPS;
-        const int ch_lo = grp * half, ch_hi = min(nchunks, ch_lo + half);
-        __half* __restrict__ out = static_cast<__half*>(p.out);
-        const __half* __restrict__ idt = p.identity;
-        float gs[4] = {0.f, 0.f, 0.f, 0.f};           // pooling partials per image of the tile (tn <= 4)
-        for (int ch = ch_lo; ch < ch_hi; ++ch) {
-          const int pix0 = ch << 4;
-          uint32_t v[16];
-          tmem_ld16(taddr + pix0, v);
-          // output coordinates of the 16 columns (uniform across the warp)
-          int img = pix0 / per_img;
-          int rem = pix0 - img * per_img;
-          int yrel = rem / p.tw, x = rem - yrel * p.tw;
-          uint32_t off[16];
-          int im[16];
-          __half idv[16];
+        if (mt * GEMM_BM + q * 32 < p.M) {              // warp-uniform: Cout is a multiple of 32
+          const float sc = p.scale[c], sh = p.shift[c];
+          const float lo = p.act == ACT_RELU ? 0.f : -INFINITY;
+          __half* __restrict__ out = static_cast<__half*>(p.out);
+          if (p.tw == p.Wout && p.tn == 1) {
+            // full-width boxes: the tile's valid pixels are consecutive NHWC rows -> linear addressing
+            const int y0 = ty * p.th;
+            const int valid = min(p.block_n, (p.Hout - y0) * p.Wout);
+            const int nchunks = (valid + 15) >> 4;
+            const int half = (nchunks + GEMM_EPI_GROUPS - 1) / GEMM_EPI_GROUPS;
+            const int ch_lo = grp * half, ch_hi = min(nchunks, ch_lo + half);
+            __half* obase = out + ((size_t)(tg * p.Hout + y0) * p.Wout) * p.M + c;
+            const size_t stride = (size_t)p.M;
+            float gsum = 0.f;
+            for (int ch = ch_lo; ch < ch_hi; ++ch) {
+              const int pix0 = ch << 4;
+              uint32_t v[16];
+              tmem_ld16(taddr + pix0, v);
+              __half* op = obase + (size_t)pix0 * stride;
+              tmem_ld_wait();
+              if (pix0 + 16 <= valid) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int n = tg * p.tn + img, y = ty * p.th + yrel;
-            const bool ok = c_ok && x < p.Wout && y < p.Hout && n < p.Nimg && img < p.tn;
-            off[j] = ok ? ((uint32_t)((n * p.Hout + y) * p.Wout + x) * (uint32_t)p.M + (uint32_t)c) : 0xFFFFFFFFu;
-            im[j] = img;
-            if (++x == p.tw) { x = 0; if (++yrel == p.th) { yrel = 0; ++img; } }
-          }
-          if (idt) {
+                for (int j = 0; j < 16; ++j) {
+                  const float raw = __uint_as_float(v[j]);
+                  const float val = fmaxf(fmaf(raw, sc, sh), lo);
+                  gsum += p.gap_raw ? raw : val;
+                  op[(size_t)j * stride] = __float2half_rn(val);
+                }
+              } else {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) idv[j] = off[j] != 0xFFFFFFFFu ? idt[off[j]] : __float2half(0.f);
-          }
-          tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            if (off[j] != 0xFFFFFFFFu) {
-              const float raw = __uint_as_float(v[j]);
-              float val = fmaf(raw, sc, sh);
-              if (idt) val += __half2float(idv[j]);
-              if (p.act == ACT_RELU) val = fmaxf(val, 0.f);
-              const float g = p.gap_raw ? raw : val;
-              gs[0] += im[j] == 0 ? g : 0.f; gs[1] += im[j] == 1 ? g : 0.f;
-              gs[2] += im[j] == 2 ? g : 0.f; gs[3] += im[j] == 3 ? g : 0.f;
-              out[off[j]] = __float2half_rn(val);
+                for (int j = 0; j < 16; ++j) {
+                  if (pix0 + j < valid) {
+                    const float raw = __uint_as_float(v[j]);
+                    const float val = fmaxf(fmaf(raw, sc, sh), lo);
+                    gsum += p.gap_raw ? raw : val;
+                    op[(size_t)j * stride] = __float2half_rn(val);
+                  }
+                }
+              }
             }
-          }
-        }
-        if (p.gap_partial && c_ok) {
+            if (p.gap_partial)
+              p.gap_partial[((size_t)tg * p.tiles_y * GEMM_EPI_GROUPS + ty * GEMM_EPI_GROUPS + grp) * p.M + c] = gsum;
+          } else {
+            // overhanging boxes (7x7 maps in 8x8x4 boxes): per-pixel coordinates and masks
+            const int per_img = p.tw * p.th;
+            const int nchunks = p.block_n >> 4;
+            const int half = (nchunks + GEMM_EPI_GROUPS - 1) / GEMM_EPI_GROUPS;
+            const int ch_lo = grp * half, ch_hi = min(nchunks, ch_lo + half);
+            float gs[4] = {0.f, 0.f, 0.f, 0.f};         // pooling partials per image of the tile (tn <= 4)
+            for (int ch = ch_lo; ch < ch_hi; ++ch) {
+              const int pix0 = ch << 4;
+              uint32_t v[16];
+              tmem_ld16(taddr + pix0, v);
+              int img = pix0 / per_img;
+              const int rem = pix0 - img * per_img;
+              int yrel = rem / p.tw, x = rem - yrel * p.tw;
+              tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int n = tg * p.tn + i;
-            if (i < p.tn && n < p.Nimg)
-              p.gap_partial[((size_t)n * p.tiles_y * GEMM_EPI_GROUPS + ty * GEMM_EPI_GROUPS + grp) * p.M + c] = gs[i];
+              for (int j = 0; j < 16; ++j) {
+                const int n = tg * p.tn + img, y = ty * p.th + yrel;
+                if (x < p.Wout && y < p.Hout && n < p.Nimg) {
+                  const float raw = __uint_as_float(v[j]);
+                  const float val = fmaxf(fmaf(raw, sc, sh), lo);
+                  const float g = p.gap_raw ? raw : val;
+                  gs[0] += img == 0 ? g : 0.f; gs[1] += img == 1 ? g : 0.f;
+                  gs[2] += img == 2 ? g : 0.f; gs[3] += img == 3 ? g : 0.f;
+                  out[((size_t)(n * p.Hout + y) * p.Wout + x) * p.M + c] = __float2half_rn(val);
+                }
+                if (++x == p.tw) { x = 0; if (++yrel == p.th) { yrel = 0; ++img; } }
+              }
+            }
+            if (p.gap_partial) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const int n = tg * p.tn + i;
+                if (i < p.tn && n < p.Nimg)
+                  p.gap_partial[((size_t)n * p.tiles_y * GEMM_EPI_GROUPS + ty * GEMM_EPI_GROUPS + grp) * p.M + c] = gs[i];
+              }
+            }
           }
         }
       }
@@ -424,7 +463,9 @@ PFN_encodeTiled get_encode_tiled();
 int make_tmap_f16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                   const uint32_t* box, const uint32_t* elem_strides);
 
-int launch_gemm(const CUtensorMap& map_a, const CUtensorMap& map_b, const GemmParams& p, int sm_count, cudaStream_t st);
+// map_eye / map_idt are only read when p.idt_blocks != 0 (pass nullptr otherwise)
+int launch_gemm(const CUtensorMap& map_a, const CUtensorMap& map_b, const GemmParams& p, int sm_count, cudaStream_t st,
+                const CUtensorMap* map_eye = nullptr, const CUtensorMap* map_idt = nullptr);
 int pick_stages(int block_n);
 
 // SIMT check kernels (gemm_ref.cuh), launched from other translation units through these wrappers

@@ -27,6 +27,8 @@ struct Bottleneck { ConvW c1, c2, c3, ds; bool has_ds = false; };
 
 struct ResNetWeights {
   ConvW stem;
+  __half* eye = nullptr;          // [128][128] one-hot A operand for the tensor-core residual add
+  CUtensorMap map_eye;
   std::vector<Bottleneck> blocks;
   std::vector<void*> allocs;
 };
@@ -161,18 +163,24 @@ static int load_conv(ResNetWeights* rw, const TensorMap& t, const std::string& c
   if (wi->second.second != (int64_t)Cout * Cin * R * R || g->second.second != Cout) return B200VQA_EINVAL;
   const bool stem = (Cin == 3);
   const int K = stem ? 192 : R * R * Cin;
-  std::vector<__half> w((size_t)Cout * K, __float2half(0.f));
-  const float* src = wi->second.first;                     // [Cout][Cin][R][S]
-  for (int o = 0; o < Cout; ++o)
-    for (int c = 0; c < Cin; ++c)
-      for (int r = 0; r < R; ++r)
-        for (int s = 0; s < R; ++s)
-          w[(size_t)o * K + ((size_t)r * R + s) * Cin + c] = __float2half_rn(src[(((size_t)o * Cin + c) * R + r) * R + s]);
   std::vector<float> sc(Cout), sh(Cout);
   for (int o = 0; o < Cout; ++o) {
     const float inv = 1.0f / sqrtf(v->second.first[o] + 1e-5f);
     sc[o] = g->second.first[o] * inv;
     sh[o] = b->second.first[o] - m->second.first[o] * sc[o];
+  }
+  // BN scale is folded into the fp16 weights (in fp32, one rounding) so that the residual identity can be
+  // accumulated by the tensor core next to the convolution.  The stem keeps its scale in the epilogue
+  // because its hook is the raw, pre-BN convolution output.
+  std::vector<__half> w((size_t)Cout * K, __float2half(0.f));
+  const float* src = wi->second.first;                     // [Cout][Cin][R][S]
+  for (int o = 0; o < Cout; ++o) {
+    const float fold = stem ? 1.0f : sc[o];
+    for (int c = 0; c < Cin; ++c)
+      for (int r = 0; r < R; ++r)
+        for (int s = 0; s < R; ++s)
+          w[(size_t)o * K + ((size_t)r * R + s) * Cin + c] = __float2half_rn(src[(((size_t)o * Cin + c) * R + r) * R + s] * fold);
+    if (!stem) sc[o] = 1.0f;
   }
   out->Cin = Cin; out->Cout = Cout; out->R = out->S = R; out->stride = stride; out->pad = pad; out->K = K;
   int rc;
@@ -199,6 +207,7 @@ static Geo geo_for(int Wout) {
 // in: NHWC fp16 [N][Hin][Win][Cin] (or the stem patch matrix); out: [N][Hout][Wout][Cout]
 static int run_conv(b200vqa_ctx* h, const ConvW& cw, const __half* in, int Nimg, int Hin, int Win, __half* out,
                     const __half* identity, int relu, float* gap_partial, int gap_raw, cudaStream_t st) {
+  const ResNetWeights& rw = *h->resnet;
   const bool stem = (cw.Cin == 3);
   const int Hout = stem ? 112 : (Hin + 2 * cw.pad - cw.R) / cw.stride + 1;
   const int Wout = stem ? 112 : (Win + 2 * cw.pad - cw.S) / cw.stride + 1;
@@ -222,7 +231,7 @@ static int run_conv(b200vqa_ctx* h, const ConvW& cw, const __half* in, int Nimg,
   p.tw = g.tw; p.th = g.th; p.tn = g.tn;
   p.Hout = Hout; p.Wout = Wout; p.Nimg = Nimg;
   p.epi = EPI_CONV; p.act = relu ? ACT_RELU : ACT_NONE; p.M = cw.Cout;
-  p.out = out; p.scale = cw.scale; p.shift = cw.shift; p.identity = identity;
+  p.out = out; p.scale = cw.scale; p.shift = cw.shift; p.idt_blocks = identity ? 2 : 0;
   p.gap_partial = gap_partial; p.gap_raw = gap_raw;
   CUtensorMap mb;
   int rc;
@@ -238,6 +247,15 @@ static int run_conv(b200vqa_ctx* h, const ConvW& cw, const __half* in, int Nimg,
     rc = make_tmap_f16(&mb, in, 4, dims, strides, box, es);
   }
   if (rc) return rc;
+  if (identity) {
+    if (cw.Cout % GEMM_BM) return B200VQA_EINVAL;
+    CUtensorMap mi;
+    uint64_t dims[4] = {(uint64_t)cw.Cout, (uint64_t)Wout, (uint64_t)Hout, (uint64_t)Nimg};
+    uint64_t strides[3] = {(uint64_t)cw.Cout * 2, (uint64_t)Wout * cw.Cout * 2, (uint64_t)Hout * Wout * cw.Cout * 2};
+    uint32_t box[4] = {GEMM_BK, (uint32_t)g.tw, (uint32_t)g.th, (uint32_t)g.tn};
+    if ((rc = make_tmap_f16(&mi, identity, 4, dims, strides, box, nullptr))) return rc;
+    return launch_gemm(cw.map_a, mb, p, h->sm_count, st, &rw.map_eye, &mi);
+  }
   return launch_gemm(cw.map_a, mb, p, h->sm_count, st);
 }
 
@@ -276,6 +294,14 @@ extern "C" int b200vqa_load_resnet50(b200vqa_t* h, int n, const char* const* nam
       rw->blocks.push_back(bk);
       inplanes = planes * 4;
     }
+  }
+  if (!rc) {
+    std::vector<__half> eye(128 * 128, __float2half(0.f));
+    for (int i = 0; i < 128; ++i) eye[i * 128 + i] = __float2half(1.0f);
+    rc = upload(rw, eye.data(), eye.size() * sizeof(__half), (void**)&rw->eye);
+    uint64_t dims[2] = {128, 128}, strides[1] = {128 * 2};
+    uint32_t box[2] = {GEMM_BK, GEMM_BM};
+    if (!rc) rc = make_tmap_f16(&rw->map_eye, rw->eye, 2, dims, strides, box, nullptr);
   }
   if (rc) { free_resnet(rw); return rc; }
   free_resnet(h->resnet);

@@ -78,7 +78,7 @@ int launch_gemm(const CUtensorMap& map_a, const CUtensorMap& map_b, const GemmPa
 
 int pick_stages(int block_n) {
   const size_t per = GEMM_BM * GEMM_BK * 2 + (size_t)block_n * GEMM_BK * 2;
-  int s = (int)((220 * 1024) / per);
+  int s = (int)((227 * 1024 - 1024 - 256 - GEMM_EPI_WARPS * 32 * EPI_LD * 4) / per);
   if (s > 6) s = 6;
   return s;
 }

@@ -37,6 +37,7 @@ constexpr int GEMM_EPI_WARPS = 8;               // two warps per TMEM lane quadr
 constexpr int GEMM_EPI_GROUPS = GEMM_EPI_WARPS / 4;
 constexpr int GEMM_THREADS = 128 + 32 * GEMM_EPI_WARPS;
 constexpr int GEMM_MAX_STAGES = 8;
+constexpr int EPI_LD = 20;                       // staging row stride (floats): 16 columns + 4 pad, keeps float4 alignment
 constexpr uint32_t GEMM_TMEM_COLS = 512;      // two accumulator stages of up to 256 columns
 
 enum { EPI_ROW = 0, EPI_CONV = 1 };
@@ -172,6 +173,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   uint64_t* tmem_full = empty_bar + GEMM_MAX_STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  float* epi_stage = reinterpret_cast<float*>(tmem_slot + 4);        // [GEMM_EPI_WARPS][32][EPI_LD] fp32, 16-byte aligned
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_tiles = p.m_tiles * p.n_tiles;
@@ -276,56 +278,49 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         const int m = mt * GEMM_BM + row;
         const int n0 = nt * p.block_n;
         if ((p.block_n & 31) == 0 && n0 + p.block_n <= p.N) {
-          // fast path: 32-column chunks, interleaved between the two warps of a quadrant
-          for (int c0 = grp * 32; c0 < p.block_n; c0 += 32 * GEMM_EPI_GROUPS) {
-            uint32_t v[32];
-            tmem_ld32(taddr + c0, v);
-            const int n = n0 + c0;
-            const size_t o = (size_t)m * p.ldo + n;
-            float4 r4[8];
-            if (p.residual && m < p.M) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) r4[j] = *reinterpret_cast<const float4*>(p.residual + o + 4 * j);
-            }
+          // fast path.  The accumulator arrives one row per thread; a warp-private 32 x 16 fp32 staging tile in
+          // shared memory transposes it so that every global access covers whole 64-byte row segments
+          // (8 rows per instruction) instead of 32 different cache lines.  16-column chunks alternate between the
+          // two warps of a quadrant.  Bias / activation / residual are applied after the transposition.
+          float* stg = epi_stage + (warp - 4) * (32 * EPI_LD);
+          const int tr = lane >> 2, tc = (lane & 3) * 4;      // transposed ownership: row i*8 + tr, columns tc..tc+3
+          const int m_base = mt * GEMM_BM + q * 32;
+          for (int c0 = grp * 16; c0 < p.block_n; c0 += 16 * GEMM_EPI_GROUPS) {
+            uint32_t v[16];
+            tmem_ld16(taddr + c0, v);
+            const int n = n0 + c0 + tc;
+            float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p.bias) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
             tmem_ld_wait();
-            if (m < p.M) {
-              float f[32];
 #pragma unroll
-              for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-              if (p.bias) {
+            for (int j = 0; j < 4; ++j)
+              *reinterpret_cast<float4*>(stg + lane * EPI_LD + 4 * j) =
+                  make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+            __syncwarp();
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                  const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n + j));
-                  f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
+            for (int i = 0; i < 4; ++i) {
+              const int r = i * 8 + tr;
+              const int mm = m_base + r;
+              float4 x = *reinterpret_cast<const float4*>(stg + r * EPI_LD + tc);
+              if (mm < p.M) {
+                x.x += b4.x; x.y += b4.y; x.z += b4.z; x.w += b4.w;
+                if (p.act == ACT_GELU) { x.x = gelu_erf(x.x); x.y = gelu_erf(x.y); x.z = gelu_erf(x.z); x.w = gelu_erf(x.w); }
+                else if (p.act == ACT_RELU) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
+                const size_t o = (size_t)mm * p.ldo + n;
+                if (p.residual) {
+                  const float4 r4 = *reinterpret_cast<const float4*>(p.residual + o);
+                  x.x += r4.x; x.y += r4.y; x.z += r4.z; x.w += r4.w;
                 }
-              }
-              if (p.act == ACT_GELU) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
-              } else if (p.act == ACT_RELU) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
-              }
-              if (p.residual) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) { f[4 * j] += r4[j].x; f[4 * j + 1] += r4[j].y; f[4 * j + 2] += r4[j].z; f[4 * j + 3] += r4[j].w; }
-              }
-              if (p.out_is_f32) {
-                float4* op = reinterpret_cast<float4*>(static_cast<float*>(p.out) + o);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) op[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
-              } else {
-                uint32_t h[16];
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                  __half2 t = __floats2half2_rn(f[2 * j], f[2 * j + 1]);
-                  h[j] = *reinterpret_cast<uint32_t*>(&t);
+                if (p.out_is_f32) {
+                  *reinterpret_cast<float4*>(static_cast<float*>(p.out) + o) = x;
+                } else {
+                  __half2 h0 = __floats2half2_rn(x.x, x.y), h1 = __floats2half2_rn(x.z, x.w);
+                  *reinterpret_cast<uint2*>(static_cast<__half*>(p.out) + o) =
+                      make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
                 }
-                uint4* op = reinterpret_cast<uint4*>(static_cast<__half*>(p.out) + o);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) op[j] = make_uint4(h[4 * j], h[4 * j + 1], h[4 * j + 2], h[4 * j + 3]);
               }
             }
+            __syncwarp();
           }
         } else {
           // generic path (ragged N / odd tile widths): 16-column chunks, scalar tail
@@ -450,7 +445,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 #endif  // B200VQA_GEMM_KERNEL_TU
 
 inline size_t gemm_smem_bytes(int block_n, int stages) {
-  return (size_t)stages * (GEMM_BM * GEMM_BK * 2 + (size_t)block_n * GEMM_BK * 2) + (2 * GEMM_MAX_STAGES + 4) * 8 + 16 + 1024;
+  return (size_t)stages * (GEMM_BM * GEMM_BK * 2 + (size_t)block_n * GEMM_BK * 2) + (2 * GEMM_MAX_STAGES + 4) * 8 + 16 +
+         (size_t)GEMM_EPI_WARPS * 32 * EPI_LD * 4 + 1024;
 }
 
 // ---------------------------------------------------------------- host: TMA descriptors

@@ -2,9 +2,9 @@
 //
 //   D[128 x BN] (fp32, TMEM) += A[128 x 64] (fp16, smem, K-major, SW128) * B[BN x 64]^T
 //
-// Roles (384 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane),
-// warp 2 = TMEM allocator, warps 4-11 = epilogue (TMEM -> registers -> global; two warps per
-// TMEM lane quadrant, each taking half of the accumulator columns).
+// Roles (512 threads): warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane),
+// warp 2 = TMEM allocator, warps 4-15 = epilogue (TMEM -> registers -> global; three warps per
+// TMEM lane quadrant, each taking a share of the accumulator columns).
 // Three pipelines: smem full/empty ring (TMA <-> MMA), TMEM full/empty double buffer
 // (MMA <-> epilogue), static round-robin tile scheduler (tile = blockIdx.x + i*gridDim.x).
 //
@@ -33,7 +33,7 @@ namespace b200vqa {
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
-constexpr int GEMM_EPI_WARPS = 8;               // two warps per TMEM lane quadrant
+constexpr int GEMM_EPI_WARPS = 12;              // three warps per TMEM lane quadrant
 constexpr int GEMM_EPI_GROUPS = GEMM_EPI_WARPS / 4;
 constexpr int GEMM_THREADS = 128 + 32 * GEMM_EPI_WARPS;
 constexpr int GEMM_MAX_STAGES = 8;
@@ -160,7 +160,7 @@ __device__ __forceinline__ uint32_t make_idesc(int n) {
 // bottleneck of the ViT MLP (see profiles/).
 __device__ __forceinline__ float gelu_erf(float x) {
   const float z = fabsf(x) * 0.70710678118654752440f;
-  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
   float poly = fmaf(1.061405429f, t, -1.453152027f);
   poly = fmaf(poly, t, 1.421413741f);
   poly = fmaf(poly, t, -0.284496736f);

@@ -22,6 +22,7 @@ class Clip:
     Pair i is (frames[i], nexts[i]); Tp <= Tf."""
     frames: torch.Tensor
     nexts: torch.Tensor
+    ready: Optional[torch.cuda.Event] = None     # recorded on the copy stream when the frames were staged asynchronously
 
 
 class Engine:
@@ -72,6 +73,8 @@ class Engine:
         full_rn, full_vt, oris, mers = [], [], [], []
         full_off, pair_off = [0], [0]
         for c in clips:
+            if c.ready is not None:
+                torch.cuda.current_stream(self.device).wait_event(c.ready)
             tp = c.nexts.shape[0]
             ori, mer = self.fragments(c.frames[:tp], c.nexts)
             oris.append(ori)
@@ -109,8 +112,23 @@ class Engine:
         return feats, score
 
     def predict_host(self, host_clips: Sequence[Sequence[torch.Tensor]], video_type=None):
-        """End-to-end entry with HOST (pinned) uint8 buffers: H2D copies, full path, D2H of the scores."""
-        clips = [Clip(f.to(self.device, non_blocking=True), n.to(self.device, non_blocking=True)) for f, n in host_clips]
+        """End-to-end entry with HOST (pinned) uint8 buffers: H2D copies, full path, D2H of the scores.
+        Copies are queued on a side stream, one event per clip, so the copy of clip i+1 overlaps the
+        fragment stages of clip i on the compute stream."""
+        if not hasattr(self, "_copy_stream"):
+            self._copy_stream = torch.cuda.Stream(self.device)
+        main = torch.cuda.current_stream(self.device)
+        self._copy_stream.wait_stream(main)
+        clips = []
+        for f, n in host_clips:
+            with torch.cuda.stream(self._copy_stream):
+                df = f.to(self.device, non_blocking=True)
+                dn = n.to(self.device, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(self._copy_stream)
+            df.record_stream(main)
+            dn.record_stream(main)
+            clips.append(Clip(df, dn, ev))
         feats, score = self.predict(clips, video_type)
         return feats, score.cpu()
 

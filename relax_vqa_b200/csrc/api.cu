@@ -66,7 +66,7 @@ extern "C" int b200vqa_destroy(b200vqa_t* h) {
   if (!h) return B200VQA_EINVAL;
   cudaSetDevice(h->device);
   cudaDeviceSynchronize();
-  for (auto& kv : h->resize_tables) { cudaFree(kv.second.d_bounds); cudaFree(kv.second.d_kk); }
+  for (auto& kv : h->resize_tables) { cudaFree(kv.second.d_bounds); cudaFree(kv.second.d_kk); cudaFree(kv.second.d_kkT); }
   h->ws_resize.release(); h->ws_flow.release(); h->ws_resnet.release(); h->ws_vit.release(); h->ws_head.release(); h->ws_misc.release();
   for (auto& ev : h->prof_events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
   for (auto& ev : h->prof_pool) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }

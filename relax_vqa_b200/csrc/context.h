@@ -12,7 +12,8 @@ namespace b200vqa {
 struct ResizeTable {          // Pillow coefficients for one (in_size -> 224, filter)
   int ksize = 0;
   int* d_bounds = nullptr;    // [224][2] (xmin, count)
-  int* d_kk = nullptr;        // [224][ksize] 22-bit fixed point
+  int* d_kk = nullptr;        // [224][ksize] 22-bit fixed point (row-major: vertical pass, broadcast reads)
+  int* d_kkT = nullptr;       // [ksize][224] tap-major copy (horizontal pass: coalesced across output columns)
 };
 
 struct DeviceBuffer {         // grow-only scratch

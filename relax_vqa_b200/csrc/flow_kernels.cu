@@ -110,19 +110,28 @@ __global__ void __launch_bounds__(256)
 k4_polyexp(const float* __restrict__ I, const uint8_t* __restrict__ gray0, const uint8_t* __restrict__ gray1, int B, int h, int w,
            PolyConsts pc, float4* __restrict__ RA, float* __restrict__ RB) {
   __shared__ float tile[PE_LH][PE_LW + 1];
-  __shared__ float v0[PE_TH][PE_LW + 1], v1[PE_TH][PE_LW + 1], v2[PE_TH][PE_LW + 1];
+  __shared__ __align__(16) float v0[PE_TH][PE_LW + 2], v1[PE_TH][PE_LW + 2], v2[PE_TH][PE_LW + 2];   // stride 76: float4 rows
   __shared__ float hrow[kFromGray ? PE_LH + 2 : 1][kFromGray ? PE_LW + 3 : 1];
   const int x0 = blockIdx.x * PE_TW, y0 = blockIdx.y * PE_TH, z = blockIdx.z;
   const int tid = threadIdx.x, wrp = tid >> 5, lane = tid & 31;
   if (kFromGray) {
     const uint8_t* g = (z < B ? gray0 + (size_t)z * h * w : gray1 + (size_t)(z - B) * h * w);
     // row-filtered gray at raw coordinates (y0-6+ty, x0-5+tx): rows 0..27, cols 0..73
-    for (int ty = wrp; ty < PE_LH + 2; ty += 8) {
-      const uint8_t* grow = g + (size_t)reflect101(min(max(y0 - 6 + ty, -1), h), h) * w;
-      for (int tx = lane; tx < PE_LW; tx += 32) {
-        const int cx = min(max(x0 - PE_N + tx, 0), w - 1);            // I is replicated outside the image
-        const float a = (float)grow[reflect101(cx - 1, w)], b = (float)grow[cx], c = (float)grow[reflect101(cx + 1, w)];
-        hrow[ty][tx] = 0.25f * a + 0.5f * b + 0.25f * c;
+    const bool interior = x0 - PE_N - 1 >= 0 && x0 + PE_TW + PE_N + 1 <= w && y0 - 6 >= 0 && y0 + PE_TH + 6 <= h;
+    if (interior) {                                                    // no clamping / reflection needed
+      for (int ty = wrp; ty < PE_LH + 2; ty += 8) {
+        const uint8_t* grow = g + (size_t)(y0 - 6 + ty) * w + (x0 - PE_N - 1);
+        for (int tx = lane; tx < PE_LW; tx += 32)
+          hrow[ty][tx] = 0.25f * (float)grow[tx] + 0.5f * (float)grow[tx + 1] + 0.25f * (float)grow[tx + 2];
+      }
+    } else {
+      for (int ty = wrp; ty < PE_LH + 2; ty += 8) {
+        const uint8_t* grow = g + (size_t)reflect101(min(max(y0 - 6 + ty, -1), h), h) * w;
+        for (int tx = lane; tx < PE_LW; tx += 32) {
+          const int cx = min(max(x0 - PE_N + tx, 0), w - 1);          // I is replicated outside the image
+          const float a = (float)grow[reflect101(cx - 1, w)], b = (float)grow[cx], c = (float)grow[reflect101(cx + 1, w)];
+          hrow[ty][tx] = 0.25f * a + 0.5f * b + 0.25f * c;
+        }
       }
     }
     __syncthreads();
@@ -164,9 +173,16 @@ k4_polyexp(const float* __restrict__ I, const uint8_t* __restrict__ gray0, const
   {
     const int ty = tid >> 4, cg = tid & 15;
     const int gy = y0 + ty;
-    float a0[14], a1[14], a2[14];
+    float a0[16], a1[16], a2[16];
 #pragma unroll
-    for (int i = 0; i < 14; ++i) { a0[i] = v0[ty][cg * 4 + i]; a1[i] = v1[ty][cg * 4 + i]; a2[i] = v2[ty][cg * 4 + i]; }
+    for (int i = 0; i < 4; ++i) {
+      const float4 q0 = *reinterpret_cast<const float4*>(&v0[ty][cg * 4 + 4 * i]);
+      const float4 q1 = *reinterpret_cast<const float4*>(&v1[ty][cg * 4 + 4 * i]);
+      const float4 q2 = *reinterpret_cast<const float4*>(&v2[ty][cg * 4 + 4 * i]);
+      a0[4 * i] = q0.x; a0[4 * i + 1] = q0.y; a0[4 * i + 2] = q0.z; a0[4 * i + 3] = q0.w;
+      a1[4 * i] = q1.x; a1[4 * i + 1] = q1.y; a1[4 * i + 2] = q1.z; a1[4 * i + 3] = q1.w;
+      a2[4 * i] = q2.x; a2[4 * i + 1] = q2.y; a2[4 * i + 2] = q2.z; a2[4 * i + 3] = q2.w;
+    }
     const size_t plane = (size_t)h * w;
 #pragma unroll
     for (int o = 0; o < 4; ++o) {
@@ -204,7 +220,7 @@ __device__ __forceinline__ float border_w(int i, int n) {
 
 constexpr int BX_TX = 64, BX_TY = 32, BX_M = 7, BX_W = BX_TX + 2 * BX_M, BX_H = BX_TY + 2 * BX_M, BX_LD = BX_W + 1;   // 78, 46, 79
 constexpr int BX_SMEM = 5 * BX_H * BX_LD * 4;
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 k4_flow_iter(const float4* __restrict__ RA0, const float* __restrict__ RB0, const float4* __restrict__ RA1,
              const float* __restrict__ RB1, const float* __restrict__ flow_in, int h, int w, float* __restrict__ flow_out) {
   extern __shared__ float Ms[];                      // [5][46][79]; rows 0..31 become the vertical sums in place
@@ -212,43 +228,66 @@ k4_flow_iter(const float4* __restrict__ RA0, const float* __restrict__ RB0, cons
   const size_t plane = (size_t)h * w, zo = (size_t)blockIdx.z * plane;
   const float2* fin = reinterpret_cast<const float2*>(flow_in) + zo;
   const int tid = threadIdx.x, wrp = tid >> 5, lane = tid & 31;
-  // phase A: structure-tensor entries at the (replicate-clamped) halo pixels; one warp per halo row
+  // phase A: structure-tensor entries at the (replicate-clamped) halo pixels; one warp per halo row, three
+  // pixels per lane processed together so that their dependent gathers (flow -> address -> R1 taps) overlap.
   for (int ty = wrp; ty < BX_H; ty += 8) {
     const int y = min(max(y0 + ty - BX_M, 0), h - 1);
-    for (int tx = lane; tx < BX_W; tx += 32) {
-      const int x = min(max(x0 + tx - BX_M, 0), w - 1);
-      const size_t o = (size_t)y * w + x;
-      const float2 d = fin[o];
-      const float4 c0 = RA0[zo + o];
-      const float c0xy = RB0[zo + o];
-      const float dx = d.x, dy = d.y;
-      float fx = (float)x + dx, fy = (float)y + dy;
-      const int x1 = (int)floorf(fx), y1 = (int)floorf(fy);
-      fx -= (float)x1; fy -= (float)y1;
-      float r2, r3, r4, r5, r6;
-      if ((unsigned)x1 < (unsigned)(w - 1) && (unsigned)y1 < (unsigned)(h - 1)) {
-        const float a00 = (1.f - fx) * (1.f - fy), a01 = fx * (1.f - fy), a10 = (1.f - fx) * fy, a11 = fx * fy;
-        const size_t q = zo + (size_t)y1 * w + x1;
-        const float4 p00 = RA1[q], p01 = RA1[q + 1], p10 = RA1[q + w], p11 = RA1[q + w + 1];
-        const float s00 = RB1[q], s01 = RB1[q + 1], s10 = RB1[q + w], s11 = RB1[q + w + 1];
-        r2 = a00 * p00.x + a01 * p01.x + a10 * p10.x + a11 * p11.x;
-        r3 = a00 * p00.y + a01 * p01.y + a10 * p10.y + a11 * p11.y;
-        r4 = a00 * p00.z + a01 * p01.z + a10 * p10.z + a11 * p11.z;
-        r5 = a00 * p00.w + a01 * p01.w + a10 * p10.w + a11 * p11.w;
-        r6 = a00 * s00 + a01 * s01 + a10 * s10 + a11 * s11;
-        r4 = (c0.z + r4) * 0.5f; r5 = (c0.w + r5) * 0.5f; r6 = (c0xy + r6) * 0.25f;
-      } else {
-        r2 = r3 = 0.f; r4 = c0.z; r5 = c0.w; r6 = c0xy * 0.5f;
+    const size_t yo = (size_t)y * w;
+    int xs[3]; bool act[3];
+    float2 d[3]; float4 c0[3]; float c0xy[3];
+#pragma unroll
+    for (int u = 0; u < 3; ++u) {
+      const int tx = lane + 32 * u;
+      act[u] = tx < BX_W;
+      xs[u] = min(max(x0 + tx - BX_M, 0), w - 1);
+      if (act[u]) {
+        const size_t o = yo + xs[u];
+        d[u] = fin[o]; c0[u] = RA0[zo + o]; c0xy[u] = RB0[zo + o];
       }
-      r2 = (c0.x - r2) * 0.5f;
-      r3 = (c0.y - r3) * 0.5f;
+    }
+    float fx[3], fy[3]; bool inside[3];
+    float4 p00[3], p01[3], p10[3], p11[3]; float s00[3], s01[3], s10[3], s11[3];
+#pragma unroll
+    for (int u = 0; u < 3; ++u) {
+      inside[u] = false;
+      if (act[u]) {
+        const float gx = (float)xs[u] + d[u].x, gy = (float)y + d[u].y;
+        const int x1 = (int)floorf(gx), y1 = (int)floorf(gy);
+        fx[u] = gx - (float)x1; fy[u] = gy - (float)y1;
+        inside[u] = (unsigned)x1 < (unsigned)(w - 1) && (unsigned)y1 < (unsigned)(h - 1);
+        if (inside[u]) {
+          const size_t q = zo + (size_t)y1 * w + x1;
+          p00[u] = RA1[q]; p01[u] = RA1[q + 1]; p10[u] = RA1[q + w]; p11[u] = RA1[q + w + 1];
+          s00[u] = RB1[q]; s01[u] = RB1[q + 1]; s10[u] = RB1[q + w]; s11[u] = RB1[q + w + 1];
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 3; ++u) {
+      if (!act[u]) continue;
+      const int x = xs[u];
+      const float dx = d[u].x, dy = d[u].y;
+      float r2, r3, r4, r5, r6;
+      if (inside[u]) {
+        const float a00 = (1.f - fx[u]) * (1.f - fy[u]), a01 = fx[u] * (1.f - fy[u]), a10 = (1.f - fx[u]) * fy[u], a11 = fx[u] * fy[u];
+        r2 = a00 * p00[u].x + a01 * p01[u].x + a10 * p10[u].x + a11 * p11[u].x;
+        r3 = a00 * p00[u].y + a01 * p01[u].y + a10 * p10[u].y + a11 * p11[u].y;
+        r4 = a00 * p00[u].z + a01 * p01[u].z + a10 * p10[u].z + a11 * p11[u].z;
+        r5 = a00 * p00[u].w + a01 * p01[u].w + a10 * p10[u].w + a11 * p11[u].w;
+        r6 = a00 * s00[u] + a01 * s01[u] + a10 * s10[u] + a11 * s11[u];
+        r4 = (c0[u].z + r4) * 0.5f; r5 = (c0[u].w + r5) * 0.5f; r6 = (c0xy[u] + r6) * 0.25f;
+      } else {
+        r2 = r3 = 0.f; r4 = c0[u].z; r5 = c0[u].w; r6 = c0xy[u] * 0.5f;
+      }
+      r2 = (c0[u].x - r2) * 0.5f;
+      r3 = (c0[u].y - r3) * 0.5f;
       r2 += r4 * dy + r6 * dx;
       r3 += r6 * dy + r5 * dx;
       if ((unsigned)(x - 5) >= (unsigned)(w - 10) || (unsigned)(y - 5) >= (unsigned)(h - 10)) {
         const float s = border_w(y, h) * border_w(x, w);
         r2 *= s; r3 *= s; r4 *= s; r5 *= s; r6 *= s;
       }
-      float* m = Ms + ty * BX_LD + tx;
+      float* m = Ms + ty * BX_LD + lane + 32 * u;
       m[0] = r4 * r4 + r6 * r6;
       m[BX_H * BX_LD] = (r4 + r5) * r6;
       m[2 * BX_H * BX_LD] = r5 * r5 + r6 * r6;

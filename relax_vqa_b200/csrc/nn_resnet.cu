@@ -44,25 +44,37 @@ void free_resnet(ResNetWeights* r) {
 // ToTensor + Normalize applied (zero padding is applied after normalisation, as in conv2d).
 __global__ void __launch_bounds__(256)
 k8_stem_im2col(const uint8_t* __restrict__ img, int is_bgr, __half* __restrict__ out, size_t npix) {
-  const size_t pix = (size_t)blockIdx.x * 4 + (threadIdx.x >> 6);     // 4 pixels per block, 64 threads each
+  // one thread = 8 consecutive k (one 16-byte store); 24 threads per output pixel
+  const size_t idx = (size_t)blockIdx.x * 256 + threadIdx.x;
+  const size_t pix = idx / 24;
   if (pix >= npix) return;
-  const int t = threadIdx.x & 63;
+  const int chunk = (int)(idx - pix * 24);
   const int x = pix % 112, y = (pix / 112) % 112;
   const size_t n = pix / (112 * 112);
   const float mean[3] = {0.485f, 0.456f, 0.406f}, stdv[3] = {0.229f, 0.224f, 0.225f};
-  __half* o = out + pix * 192;
-  for (int k = t; k < 192; k += 64) {
-    float v = 0.f;
-    if (k < 147) {
-      const int c = k % 3, s = (k / 3) % 7, r = k / 21;
-      const int iy = y * 2 + r - 3, ix = x * 2 + s - 3;
-      if (iy >= 0 && iy < 224 && ix >= 0 && ix < 224) {
-        const uint8_t u = img[((n * 224 + iy) * 224 + ix) * 3 + (is_bgr ? 2 - c : c)];
-        v = ((float)u / 255.0f - mean[c]) / stdv[c];
+  const uint8_t* base = img + n * (224 * 224 * 3);
+  uint32_t packed[4];
+#pragma unroll
+  for (int e = 0; e < 8; e += 2) {
+    float v[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int k = chunk * 8 + e + u;
+      float val = 0.f;
+      if (k < 147) {
+        const int c = k % 3, s = (k / 3) % 7, r = k / 21;
+        const int iy = y * 2 + r - 3, ix = x * 2 + s - 3;
+        if (iy >= 0 && iy < 224 && ix >= 0 && ix < 224) {
+          const uint8_t px = base[(iy * 224 + ix) * 3 + (is_bgr ? 2 - c : c)];
+          val = ((float)px / 255.0f - mean[c]) / stdv[c];
+        }
       }
+      v[u] = val;
     }
-    o[k] = __float2half_rn(v);
+    __half2 h = __floats2half2_rn(v[0], v[1]);
+    packed[e >> 1] = *reinterpret_cast<uint32_t*>(&h);
   }
+  *reinterpret_cast<uint4*>(out + pix * 192 + chunk * 8) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
 }
 
 // 3x3 / stride 2 / pad 1 max pooling, NHWC fp16, 8 channels (16 B) per thread
@@ -347,7 +359,7 @@ extern "C" int b200vqa_resnet50_features(b200vqa_t* h, const uint8_t* img, int B
     };
     // stem: im2col -> conv1 (hooked raw, pre-BN) -> BN+ReLU -> maxpool
     const size_t npix = (size_t)n * 12544;
-    k8_stem_im2col<<<(unsigned)((npix + 3) / 4), 256, 0, st>>>(im, is_bgr, col, npix);
+    k8_stem_im2col<<<(unsigned)((npix * 24 + 255) / 256), 256, 0, st>>>(im, is_bgr, col, npix);
     VQA_LAUNCH_CHECK();
     float* gp = add_hook(h->gemm_impl == 1 ? 1 : 56 * GEMM_EPI_GROUPS, 64, 12544);
     if ((rc = run_conv(h, rw.stem, col, n, 224, 224, c1, nullptr, 1, gp, 1, st))) return rc;

@@ -42,6 +42,11 @@ static int build_table(int in_size, int out_size, int filter, ResizeTable* t) {
   VQA_CUDA(cudaMalloc(&t->d_kk, kk.size() * sizeof(int)));
   VQA_CUDA(cudaMemcpy(t->d_bounds, bounds.data(), bounds.size() * sizeof(int), cudaMemcpyHostToDevice));
   VQA_CUDA(cudaMemcpy(t->d_kk, kk.data(), kk.size() * sizeof(int), cudaMemcpyHostToDevice));
+  std::vector<int> kkT((size_t)out_size * ksize);
+  for (int xx = 0; xx < out_size; ++xx)
+    for (int i = 0; i < ksize; ++i) kkT[(size_t)i * out_size + xx] = kk[(size_t)xx * ksize + i];
+  VQA_CUDA(cudaMalloc(&t->d_kkT, kkT.size() * sizeof(int)));
+  VQA_CUDA(cudaMemcpy(t->d_kkT, kkT.data(), kkT.size() * sizeof(int), cudaMemcpyHostToDevice));
   return B200VQA_OK;
 }
 
@@ -67,12 +72,13 @@ k7_resample_h(const uint8_t* __restrict__ src, int H, int W, const int* __restri
   __syncthreads();
   const int xx = threadIdx.x;
   const int xmin = bounds[xx * 2], cnt = bounds[xx * 2 + 1];
-  const int* k = kk + (size_t)xx * ksize;
+  const int* k = kk + xx;                             // tap-major table: kk[i * 224 + xx]
   int a0 = 1 << (kPrecisionBits - 1), a1 = a0, a2 = a0;
+  const uint8_t* p = row + xmin * 3;
+#pragma unroll 4
   for (int i = 0; i < cnt; ++i) {
-    const int c = __ldg(k + i);
-    const uint8_t* p = row + (xmin + i) * 3;
-    a0 += p[0] * c; a1 += p[1] * c; a2 += p[2] * c;
+    const int c = __ldg(k + i * 224);
+    a0 += p[3 * i] * c; a1 += p[3 * i + 1] * c; a2 += p[3 * i + 2] * c;
   }
   uint8_t* d = dst + (((size_t)b * H + y) * 224 + xx) * 3;
   if (swap_rb) { d[0] = clip8(a2); d[1] = clip8(a1); d[2] = clip8(a0); }
@@ -143,7 +149,7 @@ extern "C" int b200vqa_resize_pil(b200vqa_t* h, const uint8_t* src, int B, int H
     }
     size_t smem = (size_t)W * 3 + 16;
     if (smem > 48 * 1024) VQA_CUDA(cudaFuncSetAttribute(k7_resample_h, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k7_resample_h<<<dim3(H, B), 224, smem, st>>>(src, H, W, th->d_bounds, th->d_kk, th->ksize, hdst, need_v ? 0 : swap_rb);
+    k7_resample_h<<<dim3(H, B), 224, smem, st>>>(src, H, W, th->d_bounds, th->d_kkT, th->ksize, hdst, need_v ? 0 : swap_rb);
     VQA_LAUNCH_CHECK();
     vsrc = hdst;
   }

@@ -45,6 +45,7 @@ int make_tmap_f16(CUtensorMap* map, const void* base, int rank, const uint64_t* 
 int launch_gemm(const CUtensorMap& map_a, const CUtensorMap& map_b, const GemmParams& p, int sm_count, cudaStream_t st,
                 const CUtensorMap* map_eye, const CUtensorMap* map_idt) {
   if (p.idt_blocks && (!map_eye || !map_idt || p.idt_blocks != 2)) return B200VQA_EINVAL;
+  if (p.epi == EPI_CONV && p.tn > 1 && ((p.tw * p.th) % 16 != 0 || p.tn > 4)) return B200VQA_EINVAL;
   if (p.block_n % 16 || p.block_n < 16 || p.block_n > 256 || p.stages < 2 || p.stages > GEMM_MAX_STAGES) return B200VQA_EINVAL;
   const size_t smem = gemm_smem_bytes(p.block_n, p.stages);
   if (smem > 227 * 1024) return B200VQA_EINVAL;

@@ -405,33 +405,36 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             if (p.gap_partial)
               p.gap_partial[((size_t)tg * p.tiles_y * GEMM_EPI_GROUPS + ty * GEMM_EPI_GROUPS + grp) * p.M + c] = gsum;
           } else {
-            // overhanging boxes (7x7 maps in 8x8x4 boxes): per-pixel coordinates and masks
-            const int per_img = p.tw * p.th;
-            const int nchunks = p.block_n >> 4;
-            const int half = (nchunks + GEMM_EPI_GROUPS - 1) / GEMM_EPI_GROUPS;
-            const int ch_lo = grp * half, ch_hi = min(nchunks, ch_lo + half);
-            float gs[4] = {0.f, 0.f, 0.f, 0.f};         // pooling partials per image of the tile (tn <= 4)
-            for (int ch = ch_lo; ch < ch_hi; ++ch) {
-              const int pix0 = ch << 4;
-              uint32_t v[16];
-              tmem_ld16(taddr + pix0, v);
-              int img = pix0 / per_img;
-              const int rem = pix0 - img * per_img;
-              int yrel = rem / p.tw, x = rem - yrel * p.tw;
-              tmem_ld_wait();
+            // overhanging boxes (7x7 maps in 8x8x4 boxes): per-pixel coordinates and masks.  Whole images are
+            // assigned to the warps of a quadrant (image i -> warp group i % GROUPS) so that the pooling sum of an
+            // image never depends on its position in the batch (bit-exact batch invariance).
+            const int per_img = p.tw * p.th;                 // multiple of 16 (checked on the host)
+            const int chunks_per_img = per_img >> 4;
+            float gs[4] = {0.f, 0.f, 0.f, 0.f};             // pooling partials per image of the tile (tn <= 4)
+            for (int img = grp; img < p.tn; img += GEMM_EPI_GROUPS) {
+              const int n = tg * p.tn + img;
+              if (n >= p.Nimg) break;
+              float gsum = 0.f;
+              for (int ci = 0; ci < chunks_per_img; ++ci) {
+                const int pix0 = img * per_img + (ci << 4);
+                uint32_t v[16];
+                tmem_ld16(taddr + pix0, v);
+                const int rem = ci << 4;
+                int yrel = rem / p.tw, x = rem - yrel * p.tw;
+                tmem_ld_wait();
 #pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                const int n = tg * p.tn + img, y = ty * p.th + yrel;
-                if (x < p.Wout && y < p.Hout && n < p.Nimg) {
-                  const float raw = __uint_as_float(v[j]);
-                  const float val = fmaxf(fmaf(raw, sc, sh), lo);
-                  const float g = p.gap_raw ? raw : val;
-                  gs[0] += img == 0 ? g : 0.f; gs[1] += img == 1 ? g : 0.f;
-                  gs[2] += img == 2 ? g : 0.f; gs[3] += img == 3 ? g : 0.f;
-                  out[((size_t)(n * p.Hout + y) * p.Wout + x) * p.M + c] = __float2half_rn(val);
+                for (int j = 0; j < 16; ++j) {
+                  const int y = ty * p.th + yrel;
+                  if (x < p.Wout && y < p.Hout) {
+                    const float raw = __uint_as_float(v[j]);
+                    const float val = fmaxf(fmaf(raw, sc, sh), lo);
+                    gsum += p.gap_raw ? raw : val;
+                    out[((size_t)(n * p.Hout + y) * p.Wout + x) * p.M + c] = __float2half_rn(val);
+                  }
+                  if (++x == p.tw) { x = 0; ++yrel; }
                 }
-                if (++x == p.tw) { x = 0; if (++yrel == p.th) { yrel = 0; ++img; } }
               }
+              gs[img] = gsum;
             }
             if (p.gap_partial) {
 #pragma unroll

@@ -40,41 +40,45 @@ void free_resnet(ResNetWeights* r) {
 }
 
 // ------------------------------------------------------------------------------- kernels
-// Stem patch matrix: uint8 HWC image -> fp16 [B*112*112][192], k = (r*7 + s)*3 + c, with
-// ToTensor + Normalize applied (zero padding is applied after normalisation, as in conv2d).
+// Stem patch matrix: uint8 HWC image -> fp16 [B*112*112][192].  K layout: k = r*24 + s*3 + c for the 7 kernel
+// rows (21 taps + 3 zero pads each, so every row is three 16-byte stores), rows 7 (k = 168..191) are zero.
+// ToTensor + Normalize applied here; zero padding is applied after normalisation, as in conv2d.
 __global__ void __launch_bounds__(256)
 k8_stem_im2col(const uint8_t* __restrict__ img, int is_bgr, __half* __restrict__ out, size_t npix) {
-  // one thread = 8 consecutive k (one 16-byte store); 24 threads per output pixel
-  const size_t idx = (size_t)blockIdx.x * 256 + threadIdx.x;
-  const size_t pix = idx / 24;
+  const size_t idx = (size_t)blockIdx.x * 256 + threadIdx.x;     // one thread = one kernel row of one output pixel
+  const size_t pix = idx >> 3;
   if (pix >= npix) return;
-  const int chunk = (int)(idx - pix * 24);
+  const int r = (int)(idx & 7);
   const int x = pix % 112, y = (pix / 112) % 112;
   const size_t n = pix / (112 * 112);
+  const float inv_std[3] = {1.0f / 0.229f, 1.0f / 0.224f, 1.0f / 0.225f};
   const float mean[3] = {0.485f, 0.456f, 0.406f}, stdv[3] = {0.229f, 0.224f, 0.225f};
-  const uint8_t* base = img + n * (224 * 224 * 3);
-  uint32_t packed[4];
+  (void)inv_std;
+  float v[24];
 #pragma unroll
-  for (int e = 0; e < 8; e += 2) {
-    float v[2];
+  for (int i = 0; i < 24; ++i) v[i] = 0.f;
+  const int iy = y * 2 + r - 3;
+  if (r < 7 && iy >= 0 && iy < 224) {
+    const uint8_t* row = img + (n * 224 + iy) * (224 * 3);
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      const int k = chunk * 8 + e + u;
-      float val = 0.f;
-      if (k < 147) {
-        const int c = k % 3, s = (k / 3) % 7, r = k / 21;
-        const int iy = y * 2 + r - 3, ix = x * 2 + s - 3;
-        if (iy >= 0 && iy < 224 && ix >= 0 && ix < 224) {
-          const uint8_t px = base[(iy * 224 + ix) * 3 + (is_bgr ? 2 - c : c)];
-          val = ((float)px / 255.0f - mean[c]) / stdv[c];
+    for (int s = 0; s < 7; ++s) {
+      const int ix = x * 2 + s - 3;
+      if (ix >= 0 && ix < 224) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const uint8_t px = row[ix * 3 + (is_bgr ? 2 - c : c)];
+          v[s * 3 + c] = ((float)px / 255.0f - mean[c]) / stdv[c];
         }
       }
-      v[u] = val;
     }
-    __half2 h = __floats2half2_rn(v[0], v[1]);
-    packed[e >> 1] = *reinterpret_cast<uint32_t*>(&h);
   }
-  *reinterpret_cast<uint4*>(out + pix * 192 + chunk * 8) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+  uint32_t pk[12];
+#pragma unroll
+  for (int i = 0; i < 12; ++i) { __half2 h = __floats2half2_rn(v[2 * i], v[2 * i + 1]); pk[i] = *reinterpret_cast<uint32_t*>(&h); }
+  uint4* o = reinterpret_cast<uint4*>(out + pix * 192 + r * 24);
+  o[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+  o[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+  o[2] = make_uint4(pk[8], pk[9], pk[10], pk[11]);
 }
 
 // 3x3 / stride 2 / pad 1 max pooling, NHWC fp16, 8 channels (16 B) per thread
@@ -191,7 +195,8 @@ static int load_conv(ResNetWeights* rw, const TensorMap& t, const std::string& c
     for (int c = 0; c < Cin; ++c)
       for (int r = 0; r < R; ++r)
         for (int s = 0; s < R; ++s)
-          w[(size_t)o * K + ((size_t)r * R + s) * Cin + c] = __float2half_rn(src[(((size_t)o * Cin + c) * R + r) * R + s] * fold);
+          w[(size_t)o * K + (stem ? (size_t)r * 24 + s * 3 + c : ((size_t)r * R + s) * Cin + c)] =
+              __float2half_rn(src[(((size_t)o * Cin + c) * R + r) * R + s] * fold);
     if (!stem) sc[o] = 1.0f;
   }
   out->Cin = Cin; out->Cout = Cout; out->R = out->S = R; out->stride = stride; out->pad = pad; out->K = K;
@@ -359,7 +364,7 @@ extern "C" int b200vqa_resnet50_features(b200vqa_t* h, const uint8_t* img, int B
     };
     // stem: im2col -> conv1 (hooked raw, pre-BN) -> BN+ReLU -> maxpool
     const size_t npix = (size_t)n * 12544;
-    k8_stem_im2col<<<(unsigned)((npix * 24 + 255) / 256), 256, 0, st>>>(im, is_bgr, col, npix);
+    k8_stem_im2col<<<(unsigned)((npix * 8 + 255) / 256), 256, 0, st>>>(im, is_bgr, col, npix);
     VQA_LAUNCH_CHECK();
     float* gp = add_hook(h->gemm_impl == 1 ? 1 : 56 * GEMM_EPI_GROUPS, 64, 12544);
     if ((rc = run_conv(h, rw.stem, col, n, 224, 224, c1, nullptr, 1, gp, 1, st))) return rc;

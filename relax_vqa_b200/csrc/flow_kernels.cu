@@ -218,67 +218,64 @@ __device__ __forceinline__ float border_w(int i, int n) {
   return s;
 }
 
-constexpr int BX_TX = 64, BX_TY = 32, BX_M = 7, BX_W = BX_TX + 2 * BX_M, BX_H = BX_TY + 2 * BX_M, BX_LD = BX_W + 1;   // 78, 46, 79
+// 48 x 32 outputs per block: the 62-pixel halo row is covered by exactly two warp-wide passes (64 lanes)
+constexpr int BX_TX = 48, BX_TY = 32, BX_M = 7, BX_W = BX_TX + 2 * BX_M, BX_H = BX_TY + 2 * BX_M, BX_LD = 65;   // 62, 46
+constexpr int BX_SEG = BX_TX / 8;                                                                            // columns per warp in phase C
 constexpr int BX_SMEM = 5 * BX_H * BX_LD * 4;
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, 3)
 k4_flow_iter(const float4* __restrict__ RA0, const float* __restrict__ RB0, const float4* __restrict__ RA1,
              const float* __restrict__ RB1, const float* __restrict__ flow_in, int h, int w, float* __restrict__ flow_out) {
-  extern __shared__ float Ms[];                      // [5][46][79]; rows 0..31 become the vertical sums in place
+  extern __shared__ float Ms[];                      // [5][46][65]; rows 0..31 become the vertical sums in place
   const int x0 = blockIdx.x * BX_TX, y0 = blockIdx.y * BX_TY;
   const size_t plane = (size_t)h * w, zo = (size_t)blockIdx.z * plane;
   const float2* fin = reinterpret_cast<const float2*>(flow_in) + zo;
   const int tid = threadIdx.x, wrp = tid >> 5, lane = tid & 31;
-  // phase A: structure-tensor entries at the (replicate-clamped) halo pixels; one warp per halo row, three
-  // pixels per lane processed together so that their dependent gathers (flow -> address -> R1 taps) overlap.
+  // phase A: structure-tensor entries at the (replicate-clamped) halo pixels; one warp per halo row, two pixels
+  // per lane processed together so that their dependent gathers (flow -> address -> R1 taps) overlap.  Branch-free:
+  // out-of-image taps are clamped and blended out, lanes 62/63 of the second pass recompute column 61.
+  const float4* ra0 = RA0 + zo; const float* rb0 = RB0 + zo;
+  const float4* ra1 = RA1 + zo; const float* rb1 = RB1 + zo;
   for (int ty = wrp; ty < BX_H; ty += 8) {
     const int y = min(max(y0 + ty - BX_M, 0), h - 1);
-    const size_t yo = (size_t)y * w;
-    int xs[3]; bool act[3];
-    float2 d[3]; float4 c0[3]; float c0xy[3];
+    const int yo = y * w;
+    int xs[2], txs[2];
+    float2 d[2]; float4 c0[2]; float c0xy[2];
 #pragma unroll
-    for (int u = 0; u < 3; ++u) {
-      const int tx = lane + 32 * u;
-      act[u] = tx < BX_W;
-      xs[u] = min(max(x0 + tx - BX_M, 0), w - 1);
-      if (act[u]) {
-        const size_t o = yo + xs[u];
-        d[u] = fin[o]; c0[u] = RA0[zo + o]; c0xy[u] = RB0[zo + o];
-      }
+    for (int u = 0; u < 2; ++u) {
+      txs[u] = min(lane + 32 * u, BX_W - 1);
+      xs[u] = min(max(x0 + txs[u] - BX_M, 0), w - 1);
+      const int o = yo + xs[u];
+      d[u] = fin[o]; c0[u] = ra0[o]; c0xy[u] = rb0[o];
     }
-    float fx[3], fy[3]; bool inside[3];
-    float4 p00[3], p01[3], p10[3], p11[3]; float s00[3], s01[3], s10[3], s11[3];
+    float fx[2], fy[2], inside[2];
+    float4 p00[2], p01[2], p10[2], p11[2]; float s00[2], s01[2], s10[2], s11[2];
 #pragma unroll
-    for (int u = 0; u < 3; ++u) {
-      inside[u] = false;
-      if (act[u]) {
-        const float gx = (float)xs[u] + d[u].x, gy = (float)y + d[u].y;
-        const int x1 = (int)floorf(gx), y1 = (int)floorf(gy);
-        fx[u] = gx - (float)x1; fy[u] = gy - (float)y1;
-        inside[u] = (unsigned)x1 < (unsigned)(w - 1) && (unsigned)y1 < (unsigned)(h - 1);
-        if (inside[u]) {
-          const size_t q = zo + (size_t)y1 * w + x1;
-          p00[u] = RA1[q]; p01[u] = RA1[q + 1]; p10[u] = RA1[q + w]; p11[u] = RA1[q + w + 1];
-          s00[u] = RB1[q]; s01[u] = RB1[q + 1]; s10[u] = RB1[q + w]; s11[u] = RB1[q + w + 1];
-        }
-      }
+    for (int u = 0; u < 2; ++u) {
+      const float gx = (float)xs[u] + d[u].x, gy = (float)y + d[u].y;
+      const float flx = floorf(gx), fly = floorf(gy);
+      fx[u] = gx - flx; fy[u] = gy - fly;
+      const int x1 = (int)flx, y1 = (int)fly;
+      inside[u] = ((unsigned)x1 < (unsigned)(w - 1) && (unsigned)y1 < (unsigned)(h - 1)) ? 1.f : 0.f;
+      const int q = min(max(y1, 0), h - 2) * w + min(max(x1, 0), w - 2);
+      p00[u] = ra1[q]; p01[u] = ra1[q + 1]; p10[u] = ra1[q + w]; p11[u] = ra1[q + w + 1];
+      s00[u] = rb1[q]; s01[u] = rb1[q + 1]; s10[u] = rb1[q + w]; s11[u] = rb1[q + w + 1];
     }
 #pragma unroll
-    for (int u = 0; u < 3; ++u) {
-      if (!act[u]) continue;
+    for (int u = 0; u < 2; ++u) {
       const int x = xs[u];
       const float dx = d[u].x, dy = d[u].y;
-      float r2, r3, r4, r5, r6;
-      if (inside[u]) {
-        const float a00 = (1.f - fx[u]) * (1.f - fy[u]), a01 = fx[u] * (1.f - fy[u]), a10 = (1.f - fx[u]) * fy[u], a11 = fx[u] * fy[u];
-        r2 = a00 * p00[u].x + a01 * p01[u].x + a10 * p10[u].x + a11 * p11[u].x;
-        r3 = a00 * p00[u].y + a01 * p01[u].y + a10 * p10[u].y + a11 * p11[u].y;
-        r4 = a00 * p00[u].z + a01 * p01[u].z + a10 * p10[u].z + a11 * p11[u].z;
-        r5 = a00 * p00[u].w + a01 * p01[u].w + a10 * p10[u].w + a11 * p11[u].w;
-        r6 = a00 * s00[u] + a01 * s01[u] + a10 * s10[u] + a11 * s11[u];
-        r4 = (c0[u].z + r4) * 0.5f; r5 = (c0[u].w + r5) * 0.5f; r6 = (c0xy[u] + r6) * 0.25f;
-      } else {
-        r2 = r3 = 0.f; r4 = c0[u].z; r5 = c0[u].w; r6 = c0xy[u] * 0.5f;
-      }
+      const float a00 = (1.f - fx[u]) * (1.f - fy[u]), a01 = fx[u] * (1.f - fy[u]), a10 = (1.f - fx[u]) * fy[u], a11 = fx[u] * fy[u];
+      float r2 = a00 * p00[u].x + a01 * p01[u].x + a10 * p10[u].x + a11 * p11[u].x;
+      float r3 = a00 * p00[u].y + a01 * p01[u].y + a10 * p10[u].y + a11 * p11[u].y;
+      float r4 = a00 * p00[u].z + a01 * p01[u].z + a10 * p10[u].z + a11 * p11[u].z;
+      float r5 = a00 * p00[u].w + a01 * p01[u].w + a10 * p10[u].w + a11 * p11[u].w;
+      float r6 = a00 * s00[u] + a01 * s01[u] + a10 * s10[u] + a11 * s11[u];
+      const bool in = inside[u] != 0.f;
+      // inside: r4 = (R0.yy + r4)/2, r5 = (R0.xx + r5)/2, r6 = (R0.xy + r6)/4; outside: r2 = r3 = 0, r4 = R0.yy, r5 = R0.xx, r6 = R0.xy/2
+      r2 = in ? r2 : 0.f; r3 = in ? r3 : 0.f;
+      r4 = in ? (c0[u].z + r4) * 0.5f : c0[u].z;
+      r5 = in ? (c0[u].w + r5) * 0.5f : c0[u].w;
+      r6 = in ? (c0xy[u] + r6) * 0.25f : c0xy[u] * 0.5f;
       r2 = (c0[u].x - r2) * 0.5f;
       r3 = (c0[u].y - r3) * 0.5f;
       r2 += r4 * dy + r6 * dx;
@@ -287,7 +284,7 @@ k4_flow_iter(const float4* __restrict__ RA0, const float* __restrict__ RB0, cons
         const float s = border_w(y, h) * border_w(x, w);
         r2 *= s; r3 *= s; r4 *= s; r5 *= s; r6 *= s;
       }
-      float* m = Ms + ty * BX_LD + lane + 32 * u;
+      float* m = Ms + ty * BX_LD + txs[u];
       m[0] = r4 * r4 + r6 * r6;
       m[BX_H * BX_LD] = (r4 + r5) * r6;
       m[2 * BX_H * BX_LD] = r5 * r5 + r6 * r6;
@@ -314,22 +311,22 @@ k4_flow_iter(const float4* __restrict__ RA0, const float* __restrict__ RB0, cons
     col[(BX_TY - 1) * BX_LD] = prev;
   }
   __syncthreads();
-  // phase C: horizontal sums over 8-column segments + solve (f64 solve, as OpenCV): warp = segment, lane = row
+  // phase C: horizontal sums over BX_SEG-column segments + solve (f64 solve, as OpenCV): warp = segment, lane = row
   {
     const int rr = lane, seg = wrp;
     const int gy = y0 + rr;
     float g[5];
 #pragma unroll
     for (int c = 0; c < 5; ++c) {
-      const float* row = Ms + ((size_t)c * BX_H + rr) * BX_LD + seg * 8;
+      const float* row = Ms + ((size_t)c * BX_H + rr) * BX_LD + seg * BX_SEG;
       float s = 0.f;
 #pragma unroll
       for (int i = 0; i < 15; ++i) s += row[i];
       g[c] = s;
     }
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const int gx = x0 + seg * 8 + k;
+    for (int k = 0; k < BX_SEG; ++k) {
+      const int gx = x0 + seg * BX_SEG + k;
       if (gx < w && gy < h) {
         const double sc = 1.0 / 225.0;
         const double g11 = g[0] * sc, g12 = g[1] * sc, g22 = g[2] * sc, h1 = g[3] * sc, h2 = g[4] * sc;
@@ -339,10 +336,10 @@ k4_flow_iter(const float4* __restrict__ RA0, const float* __restrict__ RB0, cons
         f.y = (float)((g22 * h1 - g12 * h2) * idet);
         reinterpret_cast<float2*>(flow_out)[zo + (size_t)gy * w + gx] = f;
       }
-      if (k < 7) {
+      if (k < BX_SEG - 1) {
 #pragma unroll
         for (int c = 0; c < 5; ++c) {
-          const float* row = Ms + ((size_t)c * BX_H + rr) * BX_LD + seg * 8 + k;
+          const float* row = Ms + ((size_t)c * BX_H + rr) * BX_LD + seg * BX_SEG + k;
           g[c] += row[15] - row[0];
         }
       }

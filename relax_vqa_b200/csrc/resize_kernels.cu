@@ -55,14 +55,17 @@ __device__ __forceinline__ uint8_t clip8(int acc) {
   return (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 : v));
 }
 
-// horizontal pass: one block per input row; the row is staged in shared memory.
+// horizontal pass: one block per input row.  The row is staged in shared memory (coalesced 16-byte loads) and
+// repacked to one 32-bit word per pixel, so a tap costs one shared-memory load for all three channels and lanes
+// (whose windows start ~scale pixels apart) collide on at most ~2 banks instead of ~6 with packed 3-byte pixels.
 __global__ void __launch_bounds__(224)
 k7_resample_h(const uint8_t* __restrict__ src, int H, int W, const int* __restrict__ bounds, const int* __restrict__ kk,
               int ksize, uint8_t* __restrict__ dst, int swap_rb) {
-  extern __shared__ uint8_t row[];
+  extern __shared__ __align__(16) uint8_t row[];
   const int y = blockIdx.x, b = blockIdx.y;
   const uint8_t* s = src + ((size_t)b * H + y) * W * 3;
   const int nbytes = W * 3;
+  uint32_t* px = reinterpret_cast<uint32_t*>(row + ((nbytes + 15) & ~15));
   if ((nbytes & 15) == 0 && (((uintptr_t)s & 15) == 0)) {
     for (int i = threadIdx.x; i < nbytes / 16; i += blockDim.x)
       reinterpret_cast<uint4*>(row)[i] = __ldg(reinterpret_cast<const uint4*>(s) + i);
@@ -70,15 +73,19 @@ k7_resample_h(const uint8_t* __restrict__ src, int H, int W, const int* __restri
     for (int i = threadIdx.x; i < nbytes; i += blockDim.x) row[i] = s[i];
   }
   __syncthreads();
+  for (int i = threadIdx.x; i < W; i += blockDim.x)
+    px[i] = (uint32_t)row[3 * i] | ((uint32_t)row[3 * i + 1] << 8) | ((uint32_t)row[3 * i + 2] << 16);
+  __syncthreads();
   const int xx = threadIdx.x;
   const int xmin = bounds[xx * 2], cnt = bounds[xx * 2 + 1];
   const int* k = kk + xx;                             // tap-major table: kk[i * 224 + xx]
   int a0 = 1 << (kPrecisionBits - 1), a1 = a0, a2 = a0;
-  const uint8_t* p = row + xmin * 3;
+  const uint32_t* p = px + xmin;
 #pragma unroll 4
   for (int i = 0; i < cnt; ++i) {
     const int c = __ldg(k + i * 224);
-    a0 += p[3 * i] * c; a1 += p[3 * i + 1] * c; a2 += p[3 * i + 2] * c;
+    const uint32_t v = p[i];
+    a0 += (int)(v & 0xff) * c; a1 += (int)((v >> 8) & 0xff) * c; a2 += (int)(v >> 16) * c;
   }
   uint8_t* d = dst + (((size_t)b * H + y) * 224 + xx) * 3;
   if (swap_rb) { d[0] = clip8(a2); d[1] = clip8(a1); d[2] = clip8(a0); }
@@ -147,7 +154,7 @@ extern "C" int b200vqa_resize_pil(b200vqa_t* h, const uint8_t* src, int B, int H
       if ((rc = h->ws_resize.reserve((size_t)B * H * 672))) return rc;
       hdst = static_cast<uint8_t*>(h->ws_resize.ptr);
     }
-    size_t smem = (size_t)W * 3 + 16;
+    size_t smem = (((size_t)W * 3 + 15) & ~(size_t)15) + (size_t)W * 4;
     if (smem > 48 * 1024) VQA_CUDA(cudaFuncSetAttribute(k7_resample_h, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k7_resample_h<<<dim3(H, B), 224, smem, st>>>(src, H, W, th->d_bounds, th->d_kkT, th->ksize, hdst, need_v ? 0 : swap_rb);
     VQA_LAUNCH_CHECK();

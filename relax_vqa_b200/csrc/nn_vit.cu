@@ -89,7 +89,8 @@ k11_layernorm(const float* __restrict__ x, const float* __restrict__ w, const fl
 // ---- fused attention for one (image, head): S = QK^T * scale, softmax, O = PV.  fp16 operands on
 // the warp-level tensor path (197 keys fit in registers/smem), fp32 softmax.
 constexpr int AT_NP = 208, AT_LD = 72;
-constexpr int AT_SMEM = (2 * AT_NP + 4 * 16) * AT_LD * 2;
+constexpr int AT_WARPS = 8;
+constexpr int AT_SMEM = (2 * AT_NP + AT_WARPS * 16) * AT_LD * 2;
 __device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], const void* p) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(smem_u32(p)));
 }
@@ -102,7 +103,7 @@ __device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], 
 }
 __device__ __forceinline__ uint32_t pack_h2(float a, float b) { __half2 h = __floats2half2_rn(a, b); return *reinterpret_cast<uint32_t*>(&h); }
 
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(AT_WARPS * 32)
 k10_attention(const __half* __restrict__ qkv, __half* __restrict__ out, float scale) {
   extern __shared__ __align__(16) uint8_t at_smem[];
   typedef __half (*RowPtr)[AT_LD];
@@ -113,7 +114,7 @@ k10_attention(const __half* __restrict__ qkv, __half* __restrict__ out, float sc
   const int hh = blockIdx.x, b = blockIdx.y;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const __half* base = qkv + (size_t)b * VT * (3 * VD) + hh * VHD;
-  for (int i = tid; i < AT_NP * 8; i += 128) {
+  for (int i = tid; i < AT_NP * 8; i += AT_WARPS * 32) {
     const int row = i >> 3, ch = i & 7;
     uint4 kv = make_uint4(0, 0, 0, 0), vv = kv;
     if (row < VT) {
@@ -125,7 +126,7 @@ k10_attention(const __half* __restrict__ qkv, __half* __restrict__ out, float sc
   }
   __syncthreads();
   const int g = lane >> 2, t4 = lane & 3;
-  for (int qb = warp; qb < AT_NP / 16; qb += 4) {
+  for (int qb = warp; qb < AT_NP / 16; qb += AT_WARPS) {
     for (int i = lane; i < 16 * 8; i += 32) {
       const int r = i >> 3, ch = i & 7, row = qb * 16 + r;
       uint4 q = make_uint4(0, 0, 0, 0);
@@ -388,7 +389,7 @@ extern "C" int b200vqa_vitb16_features(b200vqa_t* h, const uint8_t* img, int B, 
       VQA_LAUNCH_CHECK();
       if ((rc = run_linear(h, bk.qkv, hbuf, m, big, 0, ACT_NONE, nullptr, st))) return rc;
       if (h->gemm_impl == 1) ref_attention<<<dim3(VH, n, VT), 64, 0, st>>>(big, att, 0.125f);
-      else k10_attention<<<dim3(VH, n), 128, AT_SMEM, st>>>(big, att, 0.125f);
+      else k10_attention<<<dim3(VH, n), AT_WARPS * 32, AT_SMEM, st>>>(big, att, 0.125f);
       VQA_LAUNCH_CHECK();
       if ((rc = run_linear(h, bk.proj, att, m, x, 1, ACT_NONE, x, st))) return rc;
       k11_layernorm<<<cdiv(m, 8), 256, 0, st>>>(x, bk.ln2_w, bk.ln2_b, hbuf, m);

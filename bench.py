@@ -211,8 +211,12 @@ def main():
     eng.ctx.set_profiling(False)
     step_ms = ms / args.steps
     achieved = gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "r1_gemm_traffic.json")
+    if os.path.exists(tp):          # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture
+        traffic = json.load(open(tp))["traffic_bytes_per_launch"]
     roofline = dict(bound="tensor", kernel="gemm_tcgen05_kernel", achieved=achieved, peak=peaks["tf_sustained"], unit="TFLOP/s",
-                    frac=achieved / peaks["tf_sustained"], traffic=None, peak_source=peaks["src"] + " (sustained fp16/bf16 dense)",
+                    frac=achieved / peaks["tf_sustained"], traffic=traffic, peak_source=peaks["src"] + " (sustained fp16/bf16 dense)",
                     launches_per_step=gemm_launches // 2, kernel_ms_per_step=gemm_ms / 2, share_of_step=(gemm_ms / 2) / step_ms,
                     algorithmic_gflop_per_pair=gemm_flops / 2 / (args.clips * PAIRS) / 1e9)
     if rank != 0:

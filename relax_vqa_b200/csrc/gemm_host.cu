@@ -77,6 +77,42 @@ int launch_gemm(const CUtensorMap& map_a, const CUtensorMap& map_b, const GemmPa
   return B200VQA_OK;
 }
 
+int launch_gemm_2cta(const CUtensorMap& map_a, const CUtensorMap& map_b, int M, int N, int K, const float* bias, const float* residual,
+                     void* out, int out_is_f32, int act, int sm_count, cudaStream_t st) {
+  if (N % G2_BN || K % GEMM_BK || M <= 0) return B200VQA_EINVAL;
+  Gemm2Params p{};
+  p.m2_tiles = cdiv(M, 256); p.n_tiles = N / G2_BN; p.k_blocks = K / GEMM_BK;
+  const size_t fixed = (2 * GEMM_MAX_STAGES + 4) * 8 + 16 + (size_t)GEMM_EPI_WARPS * 32 * EPI_LD * 4 + 1024;
+  p.stages = (int)((227 * 1024 - fixed) / G2_STAGE_BYTES);
+  if (p.stages > GEMM_MAX_STAGES) p.stages = GEMM_MAX_STAGES;
+  p.act = act; p.M = M; p.N = N; p.ldo = N; p.out_is_f32 = out_is_f32; p.bias = bias; p.residual = residual; p.out = out;
+  const size_t smem = (size_t)p.stages * G2_STAGE_BYTES + fixed;
+  static bool attr_set = false;
+  if (!attr_set) {
+    VQA_CUDA(cudaFuncSetAttribute(gemm2cta_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  const int tiles = p.m2_tiles * p.n_tiles;
+  int clusters = sm_count / 2;
+  if (clusters > tiles) clusters = tiles;
+  b200vqa_ctx* ctx = g_ctx;
+  std::pair<cudaEvent_t, cudaEvent_t> ev{};
+  const bool prof = ctx && ctx->profiling;
+  if (prof) {
+    if (!ctx->prof_pool.empty()) { ev = ctx->prof_pool.back(); ctx->prof_pool.pop_back(); }
+    else { VQA_CUDA(cudaEventCreate(&ev.first)); VQA_CUDA(cudaEventCreate(&ev.second)); }
+    VQA_CUDA(cudaEventRecord(ev.first, st));
+  }
+  gemm2cta_tcgen05_kernel<<<2 * clusters, GEMM_THREADS, smem, st>>>(map_a, map_b, p);
+  if (prof) {
+    VQA_CUDA(cudaEventRecord(ev.second, st));
+    ctx->prof_events.push_back(ev);
+    ctx->prof_flops += 2.0 * M * (double)N * K;
+  }
+  VQA_LAUNCH_CHECK();
+  return B200VQA_OK;
+}
+
 int pick_stages(int block_n) {
   const size_t per = GEMM_BM * GEMM_BK * 2 + (size_t)block_n * GEMM_BK * 2;
   int s = (int)((227 * 1024 - 1024 - 256 - GEMM_EPI_WARPS * 32 * EPI_LD * 4) / per);
@@ -116,6 +152,15 @@ extern "C" int b200vqa_gemm_f16(b200vqa_t* h, const void* A, const void* B, cons
   if (impl == 1) {
     return launch_ref_gemm_rowmajor(static_cast<const __half*>(A), static_cast<const __half*>(B), bias, nullptr, D, M, N, K, N,
                                     ACT_NONE, 1, st);
+  }
+  if (impl == 2) {
+    CUtensorMap ma2, mb2;
+    uint64_t da2[2] = {(uint64_t)K, (uint64_t)M}, db2[2] = {(uint64_t)K, (uint64_t)N}, sa2[1] = {(uint64_t)K * 2};
+    uint32_t box2[2] = {GEMM_BK, GEMM_BM};
+    int rc2;
+    if ((rc2 = make_tmap_f16(&ma2, A, 2, da2, sa2, box2, nullptr))) return rc2;
+    if ((rc2 = make_tmap_f16(&mb2, B, 2, db2, sa2, box2, nullptr))) return rc2;
+    return launch_gemm_2cta(ma2, mb2, M, N, K, bias, nullptr, D, 1, ACT_NONE, h->sm_count, st);
   }
   const int bn = N >= 256 ? 256 : ((N + 15) / 16) * 16;
   CUtensorMap ma, mb;

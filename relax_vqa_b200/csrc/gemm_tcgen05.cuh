@@ -169,6 +169,58 @@ __device__ __forceinline__ float gelu_erf(float x) {
   return 0.5f * x * (1.0f + copysignf(e, x));
 }
 
+// Row-mode epilogue of one accumulator tile (shared by the 1-CTA and 2-CTA kernels).  The accumulator arrives one
+// row per thread; a warp-private 32 x 16 fp32 staging tile in shared memory transposes it so that every global
+// access covers whole 64-byte row segments (8 rows per instruction) instead of 32 different cache lines.
+// 16-column chunks alternate between the warps of a quadrant.  Bias / activation / residual are applied after
+// the transposition; the residual lines are requested before the TMEM wait.
+__device__ __forceinline__ void epi_row_fast(const float* __restrict__ bias, const float* residual, void* out, int M, int ldo,
+                                             int out_is_f32, int act, int block_n, uint32_t taddr, float* stg, int m_base, int n0,
+                                             int grp, int lane) {
+  const int tr = lane >> 2, tc = (lane & 3) * 4;      // transposed ownership: row i*8 + tr, columns tc..tc+3
+  for (int c0 = grp * 16; c0 < block_n; c0 += 16 * GEMM_EPI_GROUPS) {
+    uint32_t v[16];
+    tmem_ld16(taddr + c0, v);
+    const int n = n0 + c0 + tc;
+    float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (bias) b4 = __ldg(reinterpret_cast<const float4*>(bias + n));
+    float4 r4[4];
+    if (residual) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int mm = m_base + i * 8 + tr;
+        r4[i] = mm < M ? *reinterpret_cast<const float4*>(residual + (size_t)mm * ldo + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      *reinterpret_cast<float4*>(stg + lane * EPI_LD + 4 * j) =
+          make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = i * 8 + tr;
+      const int mm = m_base + r;
+      float4 x = *reinterpret_cast<const float4*>(stg + r * EPI_LD + tc);
+      if (mm < M) {
+        x.x += b4.x; x.y += b4.y; x.z += b4.z; x.w += b4.w;
+        if (act == ACT_GELU) { x.x = gelu_erf(x.x); x.y = gelu_erf(x.y); x.z = gelu_erf(x.z); x.w = gelu_erf(x.w); }
+        else if (act == ACT_RELU) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
+        const size_t o = (size_t)mm * ldo + n;
+        if (residual) { x.x += r4[i].x; x.y += r4[i].y; x.z += r4[i].z; x.w += r4[i].w; }
+        if (out_is_f32) {
+          *reinterpret_cast<float4*>(static_cast<float*>(out) + o) = x;
+        } else {
+          __half2 h0 = __floats2half2_rn(x.x, x.y), h1 = __floats2half2_rn(x.z, x.w);
+          *reinterpret_cast<uint2*>(static_cast<__half*>(out) + o) = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
+        }
+      }
+    }
+    __syncwarp();
+  }
+}
+
 // ------------------------------------------------------------------------------ the kernel
 #ifdef B200VQA_GEMM_KERNEL_TU      // defined by gemm_host.cu only (one definition per library)
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
@@ -290,55 +342,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         const int m = mt * GEMM_BM + row;
         const int n0 = nt * p.block_n;
         if ((p.block_n & 31) == 0 && n0 + p.block_n <= p.N) {
-          // fast path.  The accumulator arrives one row per thread; a warp-private 32 x 16 fp32 staging tile in
-          // shared memory transposes it so that every global access covers whole 64-byte row segments
-          // (8 rows per instruction) instead of 32 different cache lines.  16-column chunks alternate between the
-          // two warps of a quadrant.  Bias / activation / residual are applied after the transposition.
-          float* stg = epi_stage + (warp - 4) * (32 * EPI_LD);
-          const int tr = lane >> 2, tc = (lane & 3) * 4;      // transposed ownership: row i*8 + tr, columns tc..tc+3
-          const int m_base = mt * GEMM_BM + q * 32;
-          for (int c0 = grp * 16; c0 < p.block_n; c0 += 16 * GEMM_EPI_GROUPS) {
-            uint32_t v[16];
-            tmem_ld16(taddr + c0, v);
-            const int n = n0 + c0 + tc;
-            float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (p.bias) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
-            float4 r4[4];
-            if (p.residual) {                              // issued before the TMEM wait: four lines in flight per thread
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const int mm = m_base + i * 8 + tr;
-                r4[i] = mm < p.M ? *reinterpret_cast<const float4*>(p.residual + (size_t)mm * p.ldo + n) : make_float4(0.f, 0.f, 0.f, 0.f);
-              }
-            }
-            tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              *reinterpret_cast<float4*>(stg + lane * EPI_LD + 4 * j) =
-                  make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
-            __syncwarp();
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int r = i * 8 + tr;
-              const int mm = m_base + r;
-              float4 x = *reinterpret_cast<const float4*>(stg + r * EPI_LD + tc);
-              if (mm < p.M) {
-                x.x += b4.x; x.y += b4.y; x.z += b4.z; x.w += b4.w;
-                if (p.act == ACT_GELU) { x.x = gelu_erf(x.x); x.y = gelu_erf(x.y); x.z = gelu_erf(x.z); x.w = gelu_erf(x.w); }
-                else if (p.act == ACT_RELU) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
-                const size_t o = (size_t)mm * p.ldo + n;
-                if (p.residual) { x.x += r4[i].x; x.y += r4[i].y; x.z += r4[i].z; x.w += r4[i].w; }
-                if (p.out_is_f32) {
-                  *reinterpret_cast<float4*>(static_cast<float*>(p.out) + o) = x;
-                } else {
-                  __half2 h0 = __floats2half2_rn(x.x, x.y), h1 = __floats2half2_rn(x.z, x.w);
-                  *reinterpret_cast<uint2*>(static_cast<__half*>(p.out) + o) =
-                      make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
-                }
-              }
-            }
-            __syncwarp();
-          }
+          epi_row_fast(p.bias, p.residual, p.out, p.M, p.ldo, p.out_is_f32, p.act, p.block_n, taddr, epi_stage + (warp - 4) * (32 * EPI_LD),
+                       mt * GEMM_BM + q * 32, n0, grp, lane);
         } else {
           // generic path (ragged N / odd tile widths): 16-column chunks, scalar tail
           for (int c0 = grp * 16; c0 < p.block_n; c0 += 16 * GEMM_EPI_GROUPS) {
@@ -462,6 +467,157 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   }
 }
 
+
+// =====================================================================================================
+// 2-CTA variant for the linear layers: a cluster of two CTAs (one SM pair) computes a 256 x 256 tile with
+// tcgen05.mma.cta_group::2.  Each CTA stages its own 128 rows of A and HALF of the B tile (128 of the 256
+// weight rows), so per SM the shared-memory traffic per K-block drops from 96 KB (48 written by TMA + 48 read by
+// the MMA) to 64 KB - the 1-CTA kernel is capped at ~2/3 of the tensor rate by the 128 B/clk shared-memory port.
+// Protocol: both producers signal the LEADER's full barrier (cta_group::2 TMA); the leader issues the MMAs and
+// multicasts its commits to both CTAs' empty / tmem_full barriers; both epilogues arrive on the leader's
+// tmem_empty barrier (remote mbarrier arrive).
+struct Gemm2Params {
+  int m2_tiles, n_tiles, k_blocks, stages;
+  int act, M, N, ldo, out_is_f32;
+  const float* bias; const float* residual; void* out;
+};
+constexpr int G2_BN = 256;
+constexpr uint32_t G2_STAGE_BYTES = 2 * GEMM_BM * GEMM_BK * 2;       // A 128x64 + B-half 128x64 (fp16) per CTA
+
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(const CUtensorMap* map, uint32_t leader_bar, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tcgen05_mma_f16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tcgen05_commit_2sm_mc(uint64_t* bar) {      // arrive on this barrier in both CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta) {   // arrive on `bar` of CTA `cta`
+  uint32_t ra;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(bar)), "r"(cta));
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(ra) : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+gemm2cta_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const Gemm2Params p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t a_bytes = GEMM_BM * GEMM_BK * 2;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * G2_STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + GEMM_MAX_STAGES;
+  uint64_t* tmem_full = empty_bar + GEMM_MAX_STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  float* epi_stage = reinterpret_cast<float*>(tmem_slot + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int num_tiles = p.m2_tiles * p.n_tiles;
+  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < p.stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 2 * GEMM_EPI_WARPS); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(GEMM_TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  cluster_sync_all();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================= TMA producer (both CTAs): own A rows + own half of the B rows =================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        const int m2 = tile % p.m2_tiles, nt = tile / p.m2_tiles;
+        for (int kb = 0; kb < p.k_blocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + (size_t)stage * G2_STAGE_BYTES;
+          uint8_t* sb = sa + a_bytes;
+          if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * G2_STAGE_BYTES);      // bytes of both CTAs land on the leader's barrier
+          const uint32_t leader_bar = smem_u32(&full_bar[stage]) & 0xFEFFFFFFu;
+          tma_load_2d_2sm(&map_a, leader_bar, sa, kb * GEMM_BK, m2 * 256 + (int)rank * GEMM_BM);
+          tma_load_2d_2sm(&map_b, leader_bar, sb, kb * GEMM_BK, nt * G2_BN + (int)rank * 128);
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer (leader CTA only) =================
+    if (rank == 0) {
+      const uint32_t idesc = (1u << 4) | ((uint32_t)(G2_BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        if (lane == 0) mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        __syncwarp();
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)acc * 256u;
+        for (int kb = 0; kb < p.k_blocks; ++kb) {
+          if (lane == 0) {
+            mbar_wait(&full_bar[stage], phase);
+            tcgen05_fence_after();
+            const uint32_t sa = smem_u32(smem + (size_t)stage * G2_STAGE_BYTES);
+            const uint64_t adesc = make_smem_desc(sa), bdesc = make_smem_desc(sa + a_bytes);
+#pragma unroll
+            for (int k = 0; k < GEMM_BK / 16; ++k)
+              tcgen05_mma_f16_2sm(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+            tcgen05_commit_2sm_mc(&empty_bar[stage]);
+            if (kb == p.k_blocks - 1) tcgen05_commit_2sm_mc(&tmem_full[acc]);
+          }
+          __syncwarp();
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ================= epilogue (both CTAs): own 128 rows x 256 columns =================
+    const int q = warp & 3, grp = (warp - 4) >> 2;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+      const int m2 = tile % p.m2_tiles, nt = tile / p.m2_tiles;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tcgen05_fence_after();
+      const uint32_t taddr = tmem_base + (uint32_t)acc * 256u + ((uint32_t)(q * 32) << 16);
+      epi_row_fast(p.bias, p.residual, p.out, p.M, p.ldo, p.out_is_f32, p.act, G2_BN, taddr, epi_stage + (warp - 4) * (32 * EPI_LD),
+                   m2 * 256 + (int)rank * GEMM_BM + q * 32, nt * G2_BN, grp, lane);
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(&tmem_empty[acc], 0);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tcgen05_fence_before();
+  cluster_sync_all();                      // neither CTA may exit (or free TMEM) while its peer can still touch it
+  if (warp == 2) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(GEMM_TMEM_COLS) : "memory");
+  }
+}
+
 #endif  // B200VQA_GEMM_KERNEL_TU
 
 inline size_t gemm_smem_bytes(int block_n, int stages) {
@@ -483,6 +639,11 @@ int make_tmap_f16(CUtensorMap* map, const void* base, int rank, const uint64_t* 
 int launch_gemm(const CUtensorMap& map_a, const CUtensorMap& map_b, const GemmParams& p, int sm_count, cudaStream_t st,
                 const CUtensorMap* map_eye = nullptr, const CUtensorMap* map_idt = nullptr);
 int pick_stages(int block_n);
+
+// 2-CTA (cta_group::2) linear layer: out[M][N] = act(A[M][K] W[N][K]^T + bias) (+ residual); N % 256 == 0, K % 64 == 0.
+// map_a / map_b must be built with 128-row boxes.
+int launch_gemm_2cta(const CUtensorMap& map_a, const CUtensorMap& map_b, int M, int N, int K, const float* bias, const float* residual,
+                     void* out, int out_is_f32, int act, int sm_count, cudaStream_t st);
 
 // SIMT check kernels (gemm_ref.cuh), launched from other translation units through these wrappers
 int launch_ref_gemm_rowmajor(const __half* A, const __half* B, const float* bias, const float* residual, void* out, int M, int N,

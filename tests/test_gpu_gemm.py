@@ -33,3 +33,19 @@ def test_gemm_matches_fp32_reference(ctx, mnk):
     assert err <= max(tol, 2e-3 * ref.abs().max().item() * 1e-2), (mnk, err)
     chk = ops.gemm_f16(ctx, A, B, bias, impl=1)
     assert (chk - ref).abs().max().item() <= max(tol, 1e-4)
+
+
+@pytest.mark.parametrize("mnk", [(256, 256, 64), (512, 768, 768), (197 * 5, 2304, 768), (1000, 768, 3072), (300, 3072, 768)])
+def test_gemm_2cta_matches_fp32_reference(ctx, mnk):
+    """cta_group::2 kernel (256 x 256 tile per SM pair, cluster launch, multicast commits)."""
+    from relax_vqa_b200 import ops
+    M, N, K = mnk
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    A = (torch.randn(M, K, device="cuda", generator=g) * 0.5).half()
+    B = (torch.randn(N, K, device="cuda", generator=g) * 0.5).half()
+    bias = torch.randn(N, device="cuda", generator=g)
+    ref = A.float() @ B.float().t() + bias
+    got = ops.gemm_f16(ctx, A, B, bias, impl=2)
+    torch.cuda.synchronize()
+    tol = 1e-5 * K ** 0.5 * 4 + 1e-6
+    assert (got - ref).abs().max().item() <= max(tol, 1e-4), mnk

@@ -144,12 +144,13 @@ int b200vqa_head_forward(b200vqa_t* h, const float* features, int V, float* scor
 
 /* ---- building blocks exposed for tests / profiling ------------------------------------ */
 /* D[M][N] = A[M][K] * B[N][K]^T (+bias[N]) on tcgen05; A, B fp16 row-major; D fp32. impl: 0
- * tcgen05, 1 SIMT check kernel. */
+ * tcgen05 1-CTA kernel, 1 SIMT check kernel, 2 tcgen05 2-CTA (cta_group::2) kernel (N % 256 == 0, K % 64 == 0). */
 int b200vqa_gemm_f16(b200vqa_t* h, const void* A, const void* B, const float* bias, float* D,
                      int M, int N, int K, int impl, void* stream);
 /* number of kernels launched by this context since creation (bench.py's gpu_launches) */
 int64_t b200vqa_launch_count(b200vqa_t* h);
-/* debug switch: 0 = tcgen05 (default), 1 = SIMT check kernels for every GEMM/conv */
+/* debug switch: 0 = tcgen05 (default; linear layers on the 2-CTA cta_group::2 kernel), 1 = SIMT check kernels for
+ * every GEMM/conv, 2 = tcgen05 with the 1-CTA kernel everywhere (A/B measurements) */
 int b200vqa_set_gemm_impl(b200vqa_t* h, int impl);
 /* profiling: when on, every tcgen05 GEMM/conv launch is bracketed by CUDA events on its stream.
  * b200vqa_profile_read synchronises, returns the summed device time (ms), the launch count and the

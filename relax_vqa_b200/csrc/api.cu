@@ -78,7 +78,7 @@ extern "C" int b200vqa_destroy(b200vqa_t* h) {
 extern "C" int64_t b200vqa_launch_count(b200vqa_t* h) { return h ? h->launches : -1; }
 
 extern "C" int b200vqa_set_gemm_impl(b200vqa_t* h, int impl) {
-  if (!h || (impl != 0 && impl != 1)) return B200VQA_EINVAL;
+  if (!h || impl < 0 || impl > 2) return B200VQA_EINVAL;
   h->gemm_impl = impl;
   return B200VQA_OK;
 }

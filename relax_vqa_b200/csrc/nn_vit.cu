@@ -13,7 +13,7 @@ namespace b200vqa {
 
 constexpr int VD = 768, VT = 197, VP = 196, VH = 12, VHD = 64, VDEPTH = 12, VMLP = 3072;
 
-struct Linear { int N = 0, K = 0; __half* w = nullptr; float* b = nullptr; CUtensorMap map_b; };
+struct Linear { int N = 0, K = 0; __half* w = nullptr; float* b = nullptr; CUtensorMap map_b, map_b128; };   // 256- / 128-row boxes
 struct VitBlock { float *ln1_w, *ln1_b, *ln2_w, *ln2_b; Linear qkv, proj, fc1, fc2; };
 struct ViTWeights {
   Linear patch;
@@ -293,7 +293,9 @@ static int load_linear(ViTWeights* vw, const TensorMap& t, const std::string& na
   if (rc) return rc;
   lin->N = N; lin->K = K;
   uint64_t dims[2] = {(uint64_t)K, (uint64_t)N}, strides[1] = {(uint64_t)K * 2};
-  uint32_t box[2] = {GEMM_BK, 256};
+  uint32_t box[2] = {GEMM_BK, 256}, box128[2] = {GEMM_BK, 128};
+  rc = make_tmap_f16(&lin->map_b128, lin->w, 2, dims, strides, box128, nullptr);
+  if (rc) return rc;
   return make_tmap_f16(&lin->map_b, lin->w, 2, dims, strides, box, nullptr);
 }
 
@@ -308,6 +310,8 @@ static int run_linear(b200vqa_ctx* h, const Linear& lin, const __half* A, int M,
   uint32_t box[2] = {GEMM_BK, GEMM_BM};
   int rc = make_tmap_f16(&ma, A, 2, dims, strides, box, nullptr);
   if (rc) return rc;
+  if (h->gemm_impl == 0 && lin.N % 256 == 0 && lin.K % GEMM_BK == 0)      // default: SM-pair kernel (cta_group::2)
+    return launch_gemm_2cta(ma, lin.map_b128, M, lin.N, lin.K, lin.b, residual, out, out_is_f32, act, h->sm_count, st);
   GemmParams p{};
   p.block_n = 256;
   p.m_tiles = cdiv(M, GEMM_BM); p.n_tiles = cdiv(lin.N, 256);

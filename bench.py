@@ -120,6 +120,7 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--clips", type=int, default=4, help="clips per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gemm-impl", type=int, default=0, help="0 default (2-CTA linears), 2 = 1-CTA kernel everywhere (A/B)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -138,6 +139,8 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     warmup = max(args.warmup, 3)
     eng = Engine(local, head_sd=weights.seeded_head_state_dict())
+    if args.gemm_impl:
+        eng.ctx.set_gemm_impl(args.gemm_impl)
     clips = synthetic_clips_on_device(args.clips, H, W, PAIRS, eng.device, seed=1000 + rank)
     stream = torch.cuda.current_stream()
 

@@ -2,6 +2,7 @@
 // run time, so the library has no link-time dependency on libcuda), launch, and the SIMT
 // check kernels used to validate the tensor-core path on the device.
 #include <mutex>
+#include <stdlib.h>
 #define B200VQA_GEMM_KERNEL_TU
 #include "context.h"
 #include "gemm_tcgen05.cuh"
@@ -47,13 +48,16 @@ int launch_gemm(const CUtensorMap& map_a, const CUtensorMap& map_b, const GemmPa
   if (p.idt_blocks && (!map_eye || !map_idt || p.idt_blocks != 2)) return B200VQA_EINVAL;
   if (p.epi == EPI_CONV && p.tn > 1 && ((p.tw * p.th) % 16 != 0 || p.tn > 4)) return B200VQA_EINVAL;
   if (p.block_n % 16 || p.block_n < 16 || p.block_n > 256 || p.stages < 2 || p.stages > GEMM_MAX_STAGES) return B200VQA_EINVAL;
-  const size_t smem = gemm_smem_bytes(p.block_n, p.stages);
+  size_t smem = gemm_smem_bytes(p.block_n, p.stages);
   if (smem > 227 * 1024) return B200VQA_EINVAL;
   static bool attr_set = false;
   if (!attr_set) {
     VQA_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
+  GemmParams q = p;
+  if (const char* e = getenv("B200VQA_GEMM_STAGES")) { int v = atoi(e); if (v >= 2 && v <= GEMM_MAX_STAGES && gemm_smem_bytes(p.block_n, v) <= 227 * 1024) q.stages = v; }
+  if (const char* e = getenv("B200VQA_GEMM_NOEPI")) q.dbg_skip_epilogue = atoi(e);
   const int tiles = p.m_tiles * p.n_tiles;
   const int grid = tiles < sm_count ? tiles : sm_count;
   b200vqa_ctx* ctx = g_ctx;
@@ -64,7 +68,8 @@ int launch_gemm(const CUtensorMap& map_a, const CUtensorMap& map_b, const GemmPa
     else { VQA_CUDA(cudaEventCreate(&ev.first)); VQA_CUDA(cudaEventCreate(&ev.second)); }
     VQA_CUDA(cudaEventRecord(ev.first, st));
   }
-  gemm_tcgen05_kernel<<<grid, GEMM_THREADS, smem, st>>>(map_a, map_b, map_eye ? *map_eye : map_a, map_idt ? *map_idt : map_b, p);
+  smem = gemm_smem_bytes(q.block_n, q.stages);
+  gemm_tcgen05_kernel<<<grid, GEMM_THREADS, smem, st>>>(map_a, map_b, map_eye ? *map_eye : map_a, map_idt ? *map_idt : map_b, q);
   if (prof) {
     VQA_CUDA(cudaEventRecord(ev.second, st));
     ctx->prof_events.push_back(ev);
@@ -85,6 +90,8 @@ int launch_gemm_2cta(const CUtensorMap& map_a, const CUtensorMap& map_b, int M, 
   const size_t fixed = (2 * GEMM_MAX_STAGES + 4) * 8 + 16 + (size_t)GEMM_EPI_WARPS * 32 * EPI_LD * 4 + 1024;
   p.stages = (int)((227 * 1024 - fixed) / G2_STAGE_BYTES);
   if (p.stages > GEMM_MAX_STAGES) p.stages = GEMM_MAX_STAGES;
+  if (const char* e = getenv("B200VQA_GEMM_STAGES")) { int v = atoi(e); if (v >= 2 && v <= p.stages) p.stages = v; }
+  if (const char* e = getenv("B200VQA_GEMM_NOEPI")) p.dbg_skip_epilogue = atoi(e);
   p.act = act; p.M = M; p.N = N; p.ldo = N; p.out_is_f32 = out_is_f32; p.bias = bias; p.residual = residual; p.out = out;
   const size_t smem = (size_t)p.stages * G2_STAGE_BYTES + fixed;
   static bool attr_set = false;
@@ -162,7 +169,8 @@ extern "C" int b200vqa_gemm_f16(b200vqa_t* h, const void* A, const void* B, cons
     if ((rc2 = make_tmap_f16(&mb2, B, 2, db2, sa2, box2, nullptr))) return rc2;
     return launch_gemm_2cta(ma2, mb2, M, N, K, bias, nullptr, D, 1, ACT_NONE, h->sm_count, st);
   }
-  const int bn = N >= 256 ? 256 : ((N + 15) / 16) * 16;
+  int bn = N >= 256 ? 256 : ((N + 15) / 16) * 16;
+  if (const char* e = getenv("B200VQA_GEMM_BN")) { int v = atoi(e); if (v >= 16 && v <= 256 && v % 16 == 0) bn = v; }
   CUtensorMap ma, mb;
   uint64_t da[2] = {(uint64_t)K, (uint64_t)M}, db[2] = {(uint64_t)K, (uint64_t)N}, sa[1] = {(uint64_t)K * 2};
   uint32_t boxa[2] = {GEMM_BK, GEMM_BM}, boxb[2] = {GEMM_BK, (uint32_t)bn};

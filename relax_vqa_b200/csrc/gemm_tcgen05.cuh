@@ -70,6 +70,7 @@ struct GemmParams {
   int idt_blocks;                // EPI_CONV: 0, or 2 = residual identity added by the tensor core (see kernel)
   float* gap_partial;            // EPI_CONV: [Nimg][tiles_y * GEMM_EPI_GROUPS][Cout] or null
   int gap_raw;                   // pool the raw accumulator (conv1 hook is pre-BN)
+  int dbg_skip_epilogue;         // profiling experiments only (B200VQA_GEMM_NOEPI=1): drain nothing, store nothing
 };
 
 // ------------------------------------------------------------------------------ PTX helpers
@@ -338,7 +339,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       mbar_wait(&tmem_full[acc], acc_phase);
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t)acc * 256u + ((uint32_t)(q * 32) << 16);
-      if (p.epi == EPI_ROW) {
+      if (p.dbg_skip_epilogue) {
+      } else if (p.epi == EPI_ROW) {
         const int m = mt * GEMM_BM + row;
         const int n0 = nt * p.block_n;
         if ((p.block_n & 31) == 0 && n0 + p.block_n <= p.N) {
@@ -480,6 +482,7 @@ struct Gemm2Params {
   int m2_tiles, n_tiles, k_blocks, stages;
   int act, M, N, ldo, out_is_f32;
   const float* bias; const float* residual; void* out;
+  int dbg_skip_epilogue;
 };
 constexpr int G2_BN = 256;
 constexpr uint32_t G2_STAGE_BYTES = 2 * GEMM_BM * GEMM_BK * 2;       // A 128x64 + B-half 128x64 (fp16) per CTA
@@ -601,8 +604,9 @@ gemm2cta_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
       mbar_wait(&tmem_full[acc], acc_phase);
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t)acc * 256u + ((uint32_t)(q * 32) << 16);
-      epi_row_fast(p.bias, p.residual, p.out, p.M, p.ldo, p.out_is_f32, p.act, G2_BN, taddr, epi_stage + (warp - 4) * (32 * EPI_LD),
-                   m2 * 256 + (int)rank * GEMM_BM + q * 32, nt * G2_BN, grp, lane);
+      if (!p.dbg_skip_epilogue)
+        epi_row_fast(p.bias, p.residual, p.out, p.M, p.ldo, p.out_is_f32, p.act, G2_BN, taddr, epi_stage + (warp - 4) * (32 * EPI_LD),
+                     m2 * 256 + (int)rank * GEMM_BM + q * 32, nt * G2_BN, grp, lane);
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(&tmem_empty[acc], 0);

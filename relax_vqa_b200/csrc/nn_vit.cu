@@ -367,7 +367,9 @@ extern "C" int b200vqa_vitb16_features(b200vqa_t* h, const uint8_t* img, int B, 
     VQA_CUDA(cudaFuncSetAttribute(k10_attention, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
     attr_done = true;
   }
-  const int CH = 128;
+  // images per pass: 127 x 197 tokens = 98 row-tile pairs -> the 3 / 9 / 12 column tiles of the ViT linears fill the
+  // 74 SM pairs in whole waves (294, 882, 1176 tiles), avoiding a nearly empty trailing wave
+  const int CH = 127;
   const int nb = B < CH ? B : CH;
   const size_t M = (size_t)nb * VT;
   size_t off = 0;

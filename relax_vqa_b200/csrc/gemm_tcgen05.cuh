@@ -280,6 +280,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + (size_t)stage * stage_bytes;
           uint8_t* sb = sa + a_bytes;
+          if (p.dbg_skip_epilogue & 2) {          // experiment: no loads, just hand the slot over
+            mbar_arrive(&full_bar[stage]);
+            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            continue;
+          }
           mbar_expect_tx(&full_bar[stage], stage_bytes);
           if (kb >= conv_blocks) {
             // residual identity: D[c][pix] += sum_k onehot[c][k] * identity[pix][mt*128 + 64*j + k]
@@ -317,9 +322,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
           tcgen05_fence_after();
           const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
           const uint64_t adesc = make_smem_desc(sa), bdesc = make_smem_desc(sa + a_bytes);
+          if (!(p.dbg_skip_epilogue & 4)) {
 #pragma unroll
-          for (int k = 0; k < GEMM_BK / 16; ++k)      // +32 B per K=16 step inside the swizzled row
-            tcgen05_mma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+            for (int k = 0; k < GEMM_BK / 16; ++k)      // +32 B per K=16 step inside the swizzled row
+              tcgen05_mma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+          }
           tcgen05_commit(&empty_bar[stage]);          // frees the smem slot when the MMAs retire
           if (kb == k_blocks - 1) tcgen05_commit(&tmem_full[acc]);
         }
@@ -339,7 +346,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       mbar_wait(&tmem_full[acc], acc_phase);
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t)acc * 256u + ((uint32_t)(q * 32) << 16);
-      if (p.dbg_skip_epilogue) {
+      if (p.dbg_skip_epilogue & 1) {
       } else if (p.epi == EPI_ROW) {
         const int m = mt * GEMM_BM + row;
         const int n0 = nt * p.block_n;
@@ -558,6 +565,11 @@ gemm2cta_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + (size_t)stage * G2_STAGE_BYTES;
           uint8_t* sb = sa + a_bytes;
+          if (p.dbg_skip_epilogue & 2) {          // experiment: no loads
+            if (rank == 0) mbar_arrive(&full_bar[stage]);
+            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            continue;
+          }
           if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * G2_STAGE_BYTES);      // bytes of both CTAs land on the leader's barrier
           const uint32_t leader_bar = smem_u32(&full_bar[stage]) & 0xFEFFFFFFu;
           tma_load_2d_2sm(&map_a, leader_bar, sa, kb * GEMM_BK, m2 * 256 + (int)rank * GEMM_BM);
@@ -583,9 +595,11 @@ gemm2cta_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
             tcgen05_fence_after();
             const uint32_t sa = smem_u32(smem + (size_t)stage * G2_STAGE_BYTES);
             const uint64_t adesc = make_smem_desc(sa), bdesc = make_smem_desc(sa + a_bytes);
+            if (!(p.dbg_skip_epilogue & 4)) {
 #pragma unroll
-            for (int k = 0; k < GEMM_BK / 16; ++k)
-              tcgen05_mma_f16_2sm(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+              for (int k = 0; k < GEMM_BK / 16; ++k)
+                tcgen05_mma_f16_2sm(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+            }
             tcgen05_commit_2sm_mc(&empty_bar[stage]);
             if (kb == p.k_blocks - 1) tcgen05_commit_2sm_mc(&tmem_full[acc]);
           }
@@ -604,7 +618,7 @@ gemm2cta_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
       mbar_wait(&tmem_full[acc], acc_phase);
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t)acc * 256u + ((uint32_t)(q * 32) << 16);
-      if (!p.dbg_skip_epilogue)
+      if (!(p.dbg_skip_epilogue & 1))
         epi_row_fast(p.bias, p.residual, p.out, p.M, p.ldo, p.out_is_f32, p.act, G2_BN, taddr, epi_stage + (warp - 4) * (32 * EPI_LD),
                      m2 * 256 + (int)rank * GEMM_BM + q * 32, nt * G2_BN, grp, lane);
       tcgen05_fence_before();

@@ -24,11 +24,12 @@ if __name__ == "__main__":
         us, tf = run(M, N, K, impl)
         print(json.dumps(dict(M=M, N=N, K=K, impl=impl, us=round(us, 1), tflops=round(tf, 1), env={k: v for k, v in os.environ.items() if k.startswith("B200VQA_GEMM")})))
     else:
-        shapes = [(25216, 2304, 768), (25216, 768, 3072)]
+        shapes = [(25088, 2304, 768), (8192, 8192, 8192)]
         for (M, N, K) in shapes:
-            for impl, env in [(0, {}), (0, {"B200VQA_GEMM_NOEPI": "1"}), (0, {"B200VQA_GEMM_STAGES": "2"}), (0, {"B200VQA_GEMM_STAGES": "3"}),
-                              (0, {"B200VQA_GEMM_BN": "128"}), (0, {"B200VQA_GEMM_BN": "128", "B200VQA_GEMM_NOEPI": "1"}),
-                              (2, {}), (2, {"B200VQA_GEMM_NOEPI": "1"}), (2, {"B200VQA_GEMM_STAGES": "3"}), (2, {"B200VQA_GEMM_STAGES": "4"})]:
+            # NOEPI bits: 1 = skip epilogue, 2 = skip TMA loads, 4 = skip MMA issue (pipeline-skeleton experiments)
+            for impl, env in [(0, {}), (0, {"B200VQA_GEMM_NOEPI": "1"}), (0, {"B200VQA_GEMM_NOEPI": "3"}), (0, {"B200VQA_GEMM_NOEPI": "5"}),
+                              (0, {"B200VQA_GEMM_NOEPI": "7"}), (2, {}), (2, {"B200VQA_GEMM_NOEPI": "1"}), (2, {"B200VQA_GEMM_NOEPI": "3"}),
+                              (2, {"B200VQA_GEMM_NOEPI": "5"}), (2, {"B200VQA_GEMM_NOEPI": "7"})]:
                 e = dict(os.environ); e.update(env)
                 out = subprocess.run([sys.executable, __file__, "one", str(M), str(N), str(K), str(impl)], env=e, capture_output=True, text=True)
                 print(out.stdout.strip() or out.stderr[-300:])

@@ -145,3 +145,39 @@ def test_zero_pair_video_does_not_abort_batch(engine):
     assert torch.isnan(feats[0, 15424:]).all() and not torch.isnan(feats[0, :15424]).any()
     score = ops.head_forward(engine.ctx, feats)
     assert torch.isfinite(score).all()
+
+
+def test_dataset_driver_npy_and_mat_formats(engine, tmp_path):
+    """8(f) rows 2-3: metadata CSV -> per-video .npy with the reference's names/shapes -> (N, D) .mat; resume."""
+    import pandas as pd
+    import scipy.io
+    from relax_vqa_b200 import dataset_driver as dd
+    from relax_vqa_b200.data_processing import extract_npy2mat as fmt
+    frames_root, out_root = tmp_path / "frames", tmp_path / "out"
+    vids = [("a1", 144, 256, 2), ("b2", 272, 480, 3), ("missing", 144, 256, 0)]
+    for i, (vid, h, w, t) in enumerate(vids):
+        d = frames_root / f"video_{i + 1}"
+        d.mkdir(parents=True)
+        if t:
+            fr, nx = synth.make_clip(40 + i, h, w, t)
+            for k in range(t):
+                cv2.imwrite(str(d / f"{vid}_{k + 1}.png"), fr[k])
+                cv2.imwrite(str(d / f"{vid}_{k + 1}_next.png"), nx[k])
+    csv = tmp_path / "meta.csv"
+    pd.DataFrame(dict(vid=[v[0] for v in vids], width=[v[2] for v in vids], height=[v[1] for v in vids], framerate=[29.97] * 3,
+                      nb_frames=[60] * 3)).to_csv(csv, index=False)
+    st = dd.run(str(csv), str(frames_root), str(out_root), "konvid_1k", engine=engine, batch_videos=2)
+    assert [s for _, s in st][:2] == ["done", "done"] and st[2][1].startswith("error")
+    p0 = dd.output_paths(str(out_root), "konvid_1k", 0)
+    assert np.load(p0["full_resnet"]).shape == (2, 13120) and np.load(p0["frag_resnet"]).shape == (2, 15171)
+    assert np.load(p0["full_vit"]).shape == (2, 2304) and np.load(p0["frag_vit"]).shape == (2, 4608)
+    assert os.path.basename(p0["frag_resnet"]) == "video_1_resnet50_feature_map_original.npy"
+    st2 = dd.run(str(csv), str(frames_root), str(out_root), "konvid_1k", engine=engine)
+    assert [s for _, s in st2][:2] == ["skipped", "skipped"]
+    d = fmt.features_dir(os.path.join(str(out_root), "features_merged_frag"), "resnet50", "layer_stack", "konvid_1k")
+    mat = fmt.collate(d, 2, "resnet50")
+    assert mat.shape == (2, 15171) and mat.dtype == np.float64
+    assert np.allclose(mat[1], np.load(dd.output_paths(str(out_root), "konvid_1k", 1)["frag_resnet"]).mean(0))
+    name = fmt.save_features(str(tmp_path / "mat"), "konvid_1k", mat, "resnet50")
+    assert scipy.io.loadmat(name)["konvid_1k"].shape == (2, 15171)
+    assert dd.frame_interval(29.97) == 14 and dd.frame_interval(1.5) == 1

@@ -181,3 +181,22 @@ def test_dataset_driver_npy_and_mat_formats(engine, tmp_path):
     name = fmt.save_features(str(tmp_path / "mat"), "konvid_1k", mat, "resnet50")
     assert scipy.io.loadmat(name)["konvid_1k"].shape == (2, 15171)
     assert dd.frame_interval(29.97) == 14 and dd.frame_interval(1.5) == 1
+
+
+@pytest.mark.parametrize("hw", [(100, 150), (333, 517)])
+def test_odd_resolution_clip_vs_oracle(engine, hw):
+    """LSVQ-style odd sizes: < 196 patches (zero-filled canvas), W % 16 != 0 (byte paths), shallow pyramid."""
+    from relax_vqa_b200.engine import Clip
+    fr, nx = synth.make_clip(77, hw[0], hw[1], 2)
+    rsd, vsd = weights.seeded_resnet50_state_dict(1234), weights.seeded_vitb16_state_dict(4321)
+    blocks = P.video_feature_blocks(fr, nx, rsd, vsd)
+    ref = P.video_vector(blocks)
+    clip = Clip(torch.from_numpy(fr).cuda(), torch.from_numpy(nx).cuda())
+    inter = engine.fragments(clip.frames, clip.nexts, keep_intermediates=True)
+    for t in range(2):
+        assert np.array_equal(inter["diff_frag"][t].cpu().numpy(), blocks["pairs"][t]["diff_frag"])
+        assert np.array_equal(inter["ori_frag"][t].cpu().numpy(), blocks["pairs"][t]["ori_frag"])
+        assert np.abs(inter["flow"][t].cpu().numpy() - blocks["pairs"][t]["flow"]).max() < 2e-3
+    got = engine.extract([clip])[0].cpu().numpy()
+    e = seg_err(got, ref[None], VEC_SEGS)
+    assert max(e) <= 1e-2, e

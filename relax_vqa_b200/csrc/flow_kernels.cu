@@ -145,7 +145,7 @@ k4_polyexp(const float* __restrict__ I, const uint8_t* __restrict__ gray0, const
            PolyConsts pc, float4* __restrict__ RA, float* __restrict__ RB) {
   __shared__ float tile[PE_LH][PE_LW + 1];
   __shared__ __align__(16) float v0[PE_TH][PE_LW + 2], v1[PE_TH][PE_LW + 2], v2[PE_TH][PE_LW + 2];   // stride 76: float4 rows
-  __shared__ float hrow[kFromGray ? PE_LH + 2 : 1][kFromGray ? PE_LW + 3 : 1];
+  __shared__ int hrow[kFromGray ? PE_LH + 2 : 1][kFromGray ? PE_LW + 3 : 1];   // 4 x row-filtered gray, exact integers
   const int x0 = blockIdx.x * PE_TW, y0 = blockIdx.y * PE_TH, z = blockIdx.z;
   const int tid = threadIdx.x, wrp = tid >> 5, lane = tid & 31;
   if (kFromGray) {
@@ -156,15 +156,14 @@ k4_polyexp(const float* __restrict__ I, const uint8_t* __restrict__ gray0, const
       for (int ty = wrp; ty < PE_LH + 2; ty += 8) {
         const uint8_t* grow = g + (size_t)(y0 - 6 + ty) * w + (x0 - PE_N - 1);
         for (int tx = lane; tx < PE_LW; tx += 32)
-          hrow[ty][tx] = 0.25f * (float)grow[tx] + 0.5f * (float)grow[tx + 1] + 0.25f * (float)grow[tx + 2];
+          hrow[ty][tx] = (int)grow[tx] + 2 * (int)grow[tx + 1] + (int)grow[tx + 2];
       }
     } else {
       for (int ty = wrp; ty < PE_LH + 2; ty += 8) {
         const uint8_t* grow = g + (size_t)reflect101(min(max(y0 - 6 + ty, -1), h), h) * w;
         for (int tx = lane; tx < PE_LW; tx += 32) {
           const int cx = min(max(x0 - PE_N + tx, 0), w - 1);          // I is replicated outside the image
-          const float a = (float)grow[reflect101(cx - 1, w)], b = (float)grow[cx], c = (float)grow[reflect101(cx + 1, w)];
-          hrow[ty][tx] = 0.25f * a + 0.5f * b + 0.25f * c;
+          hrow[ty][tx] = (int)grow[reflect101(cx - 1, w)] + 2 * (int)grow[cx] + (int)grow[reflect101(cx + 1, w)];
         }
       }
     }
@@ -172,7 +171,8 @@ k4_polyexp(const float* __restrict__ I, const uint8_t* __restrict__ gray0, const
     for (int ty = wrp; ty < PE_LH; ty += 8) {
       const int cy = min(max(y0 - PE_N + ty, 0), h - 1);
       const int r = cy - (y0 - 6);                                      // hrow row of image row cy
-      for (int tx = lane; tx < PE_LW; tx += 32) tile[ty][tx] = 0.25f * hrow[r - 1][tx] + 0.5f * hrow[r][tx] + 0.25f * hrow[r + 1][tx];
+      // (.25 .5 .25) x (.25 .5 .25) of 8-bit integers is exact in fp32, so integer sums / 16 are bit-identical to OpenCV's float passes
+      for (int tx = lane; tx < PE_LW; tx += 32) tile[ty][tx] = (float)(hrow[r - 1][tx] + 2 * hrow[r][tx] + hrow[r + 1][tx]) * 0.0625f;
     }
   } else {
     const float* img = I + (size_t)z * h * w;

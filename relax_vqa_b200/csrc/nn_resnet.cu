@@ -333,7 +333,7 @@ extern "C" int b200vqa_resnet50_features(b200vqa_t* h, const uint8_t* img, int B
   CtxScope scope(h);
   cudaStream_t st = as_stream(stream);
   const ResNetWeights& rw = *h->resnet;
-  const int CH = 64;                                   // images per pass (bounds the workspace)
+  const int CH = 128;                                  // images per pass (bounds the workspace; fills the 7x7 layers' tile grid)
   const int nb = B < CH ? B : CH;
   // workspace carve-up (bytes), all fp16 NHWC unless noted
   const size_t sz_col = (size_t)nb * 12544 * 192 * 2, sz_c1 = (size_t)nb * 12544 * 64 * 2, sz_big = (size_t)nb * 3136 * 256 * 2;

@@ -103,7 +103,7 @@ __device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], 
 }
 __device__ __forceinline__ uint32_t pack_h2(float a, float b) { __half2 h = __floats2half2_rn(a, b); return *reinterpret_cast<uint32_t*>(&h); }
 
-__global__ void __launch_bounds__(AT_WARPS * 32)
+__global__ void __launch_bounds__(AT_WARPS * 32, 2)
 k10_attention(const __half* __restrict__ qkv, __half* __restrict__ out, float scale) {
   extern __shared__ __align__(16) uint8_t at_smem[];
   typedef __half (*RowPtr)[AT_LD];
@@ -137,60 +137,81 @@ k10_attention(const __half* __restrict__ qkv, __half* __restrict__ out, float sc
     uint32_t qf[4][4];
 #pragma unroll
     for (int ks = 0; ks < 4; ++ks) ldsm_x4(qf[ks], &sQ[warp][lane & 15][ks * 16 + (lane >> 4) * 8]);
-    float s[AT_NP / 8][4];
+    // two key halves (112 + 96) with an online softmax: half the score registers, so two CTAs fit per SM
+    float o[8][4];
 #pragma unroll
-    for (int nt = 0; nt < AT_NP / 8; ++nt) {
-      s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+    for (int i = 0; i < 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+    float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
 #pragma unroll
-      for (int kp = 0; kp < 2; ++kp) {
-        uint32_t kb[4];
-        ldsm_x4(kb, &sK[nt * 8 + (lane & 7)][kp * 32 + (lane >> 3) * 8]);
-        mma16816(s[nt], qf[2 * kp], kb[0], kb[1]);
-        mma16816(s[nt], qf[2 * kp + 1], kb[2], kb[3]);
+    for (int half = 0; half < 2; ++half) {
+      const int key0 = half * 112;
+      constexpr int NT_MAX = 14;
+      const int ntn = half == 0 ? 14 : 12;                // n-tiles (8 keys) in this half
+      float s[NT_MAX][4];
+#pragma unroll
+      for (int nt = 0; nt < NT_MAX; ++nt) {
+        s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+        if (nt < ntn) {
+#pragma unroll
+          for (int kp = 0; kp < 2; ++kp) {
+            uint32_t kb[4];
+            ldsm_x4(kb, &sK[key0 + nt * 8 + (lane & 7)][kp * 32 + (lane >> 3) * 8]);
+            mma16816(s[nt], qf[2 * kp], kb[0], kb[1]);
+            mma16816(s[nt], qf[2 * kp + 1], kb[2], kb[3]);
+          }
+        }
       }
-    }
-    // softmax over the 197 valid keys; this thread owns rows g (regs 0,1) and g+8 (regs 2,3)
-    float m0 = -INFINITY, m1 = -INFINITY;
+      // this thread owns rows g (regs 0,1) and g+8 (regs 2,3); keys >= 197 are masked
+      float hm0 = -INFINITY, hm1 = -INFINITY;
 #pragma unroll
-    for (int nt = 0; nt < AT_NP / 8; ++nt) {
+      for (int nt = 0; nt < NT_MAX; ++nt) {
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int col = nt * 8 + t4 * 2 + (e & 1);
-        s[nt][e] = col < VT ? s[nt][e] * scale : -INFINITY;
+        for (int e = 0; e < 4; ++e) {
+          const int col = key0 + nt * 8 + t4 * 2 + (e & 1);
+          s[nt][e] = (nt < ntn && col < VT) ? s[nt][e] * scale : -INFINITY;
+        }
+        hm0 = fmaxf(hm0, fmaxf(s[nt][0], s[nt][1]));
+        hm1 = fmaxf(hm1, fmaxf(s[nt][2], s[nt][3]));
       }
-      m0 = fmaxf(m0, fmaxf(s[nt][0], s[nt][1]));
-      m1 = fmaxf(m1, fmaxf(s[nt][2], s[nt][3]));
-    }
-    m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1)); m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
-    m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
-    float l0 = 0.f, l1 = 0.f;
+      hm0 = fmaxf(hm0, __shfl_xor_sync(0xffffffffu, hm0, 1)); hm0 = fmaxf(hm0, __shfl_xor_sync(0xffffffffu, hm0, 2));
+      hm1 = fmaxf(hm1, __shfl_xor_sync(0xffffffffu, hm1, 1)); hm1 = fmaxf(hm1, __shfl_xor_sync(0xffffffffu, hm1, 2));
+      const float n0 = fmaxf(m0, hm0), n1 = fmaxf(m1, hm1);
+      const float c0 = __expf(m0 - n0), c1 = __expf(m1 - n1);     // rescale of the running sums (exp(-inf) = 0 on the first half)
+      m0 = n0; m1 = n1;
+      l0 *= c0; l1 *= c1;
 #pragma unroll
-    for (int nt = 0; nt < AT_NP / 8; ++nt) {
-      s[nt][0] = __expf(s[nt][0] - m0); s[nt][1] = __expf(s[nt][1] - m0);
-      s[nt][2] = __expf(s[nt][2] - m1); s[nt][3] = __expf(s[nt][3] - m1);
-      l0 += s[nt][0] + s[nt][1]; l1 += s[nt][2] + s[nt][3];
+      for (int i = 0; i < 8; ++i) { o[i][0] *= c0; o[i][1] *= c0; o[i][2] *= c1; o[i][3] *= c1; }
+      float h0 = 0.f, h1 = 0.f;
+#pragma unroll
+      for (int nt = 0; nt < NT_MAX; ++nt) {
+        s[nt][0] = __expf(s[nt][0] - m0); s[nt][1] = __expf(s[nt][1] - m0);
+        s[nt][2] = __expf(s[nt][2] - m1); s[nt][3] = __expf(s[nt][3] - m1);
+        h0 += s[nt][0] + s[nt][1]; h1 += s[nt][2] + s[nt][3];
+      }
+      l0 += h0; l1 += h1;                                          // per-thread partial row sums; reduced across the quad at the end
+#pragma unroll
+      for (int kk = 0; kk < NT_MAX / 2; ++kk) {
+        if (2 * kk < ntn) {
+          uint32_t pf[4];
+          pf[0] = pack_h2(s[2 * kk][0], s[2 * kk][1]);
+          pf[1] = pack_h2(s[2 * kk][2], s[2 * kk][3]);
+          pf[2] = pack_h2(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+          pf[3] = pack_h2(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+#pragma unroll
+          for (int np = 0; np < 4; ++np) {
+            uint32_t vb[4];
+            ldsm_x4_t(vb, &sV[key0 + kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8][np * 16 + (lane >> 4) * 8]);
+            mma16816(o[2 * np], pf, vb[0], vb[1]);
+            mma16816(o[2 * np + 1], pf, vb[2], vb[3]);
+          }
+        }
+      }
     }
     l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
     l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
     const float r0 = 1.f / l0, r1 = 1.f / l1;
-    float o[8][4];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
-#pragma unroll
-    for (int kk = 0; kk < AT_NP / 16; ++kk) {
-      uint32_t pf[4];
-      pf[0] = pack_h2(s[2 * kk][0] * r0, s[2 * kk][1] * r0);
-      pf[1] = pack_h2(s[2 * kk][2] * r1, s[2 * kk][3] * r1);
-      pf[2] = pack_h2(s[2 * kk + 1][0] * r0, s[2 * kk + 1][1] * r0);
-      pf[3] = pack_h2(s[2 * kk + 1][2] * r1, s[2 * kk + 1][3] * r1);
-#pragma unroll
-      for (int np = 0; np < 4; ++np) {
-        uint32_t vb[4];
-        ldsm_x4_t(vb, &sV[kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8][np * 16 + (lane >> 4) * 8]);
-        mma16816(o[2 * np], pf, vb[0], vb[1]);
-        mma16816(o[2 * np + 1], pf, vb[2], vb[3]);
-      }
-    }
+    for (int i = 0; i < 8; ++i) { o[i][0] *= r0; o[i][1] *= r0; o[i][2] *= r1; o[i][3] *= r1; }
     const int row0 = qb * 16 + g, row1 = row0 + 8;
     __half* ob = out + (size_t)b * VT * VD + hh * VHD;
 #pragma unroll

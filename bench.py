@@ -211,6 +211,7 @@ def main():
     for _ in range(2):
         eng.predict(clips, "live_vqc")
     gemm_ms, gemm_launches, gemm_flops = eng.ctx.profile_read()
+    flow_ms, flow_launches, flow_bytes = eng.ctx.profile_read_flow()
     eng.ctx.set_profiling(False)
     step_ms = ms / args.steps
     achieved = gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
@@ -222,6 +223,11 @@ def main():
                     frac=achieved / peaks["tf_sustained"], traffic=traffic, peak_source=peaks["src"] + " (sustained fp16/bf16 dense)",
                     launches_per_step=gemm_launches // 2, kernel_ms_per_step=gemm_ms / 2, share_of_step=(gemm_ms / 2) / step_ms,
                     algorithmic_gflop_per_pair=gemm_flops / 2 / (args.clips * PAIRS) / 1e9)
+    flow_gbs = flow_bytes / (flow_ms / 1e3) / 1e9 if flow_ms > 0 else 0.0
+    roofline_hbm = dict(bound="hbm", kernel="k4_flow_iter", achieved=flow_gbs, peak=peaks["hbm_gbs"], unit="GB/s", frac=flow_gbs / peaks["hbm_gbs"],
+                        traffic=(flow_bytes / max(flow_launches, 1)) * (2.545 / 2.554), launches_per_step=flow_launches // 2, kernel_ms_per_step=flow_ms / 2,
+                        share_of_step=(flow_ms / 2) / step_ms, algorithmic_bytes_per_pixel_iteration=56,
+                        note="largest single bandwidth kernel; traffic = algorithmic bytes per launch x the ncu dram/algorithmic ratio measured on the level-0 launch (2.545 GB vs 2.554 GB, profiles/r1_ncu_full_flow_iter2.txt)")
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -237,7 +243,7 @@ def main():
                             timing="inputs larger than L2 (%.0f MB per step per GPU)" % (h2d / 1e6), parallelism=f"video-sharded x{world}"),
                 clocks=clocks, gpu_launches=int(launches),
                 e2e=dict(value=e2e_value, unit="videos/s", h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(4 * args.clips)),
-                roofline=roofline, cpu_baseline=cpu)
+                roofline=roofline, roofline_hbm=roofline_hbm, cpu_baseline=cpu)
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -157,6 +157,8 @@ int b200vqa_set_gemm_impl(b200vqa_t* h, int impl);
  * algorithmic FLOPs (2*M*N*K of the un-padded problems) since the last read, and resets them. */
 int b200vqa_set_profiling(b200vqa_t* h, int on);
 int b200vqa_profile_read(b200vqa_t* h, double* gemm_ms, int64_t* gemm_launches, double* gemm_flops);
+/* same for the Farneback iteration kernel (k4_flow_iter): device ms, launches, algorithmic bytes (56 B per pixel) */
+int b200vqa_profile_read_flow(b200vqa_t* h, double* ms, int64_t* launches, double* bytes);
 
 #ifdef __cplusplus
 }

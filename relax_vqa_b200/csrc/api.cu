@@ -69,6 +69,7 @@ extern "C" int b200vqa_destroy(b200vqa_t* h) {
   for (auto& kv : h->resize_tables) { cudaFree(kv.second.d_bounds); cudaFree(kv.second.d_kk); cudaFree(kv.second.d_kkT); }
   h->ws_resize.release(); h->ws_flow.release(); h->ws_resnet.release(); h->ws_vit.release(); h->ws_head.release(); h->ws_misc.release();
   for (auto& ev : h->prof_events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
+  for (auto& ev : h->prof_events_flow) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
   for (auto& ev : h->prof_pool) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
   free_resnet(h->resnet); free_vit(h->vit); free_head(h->head);
   delete h;
@@ -86,6 +87,25 @@ extern "C" int b200vqa_set_gemm_impl(b200vqa_t* h, int impl) {
 extern "C" int b200vqa_set_profiling(b200vqa_t* h, int on) {
   if (!h) return B200VQA_EINVAL;
   h->profiling = on ? 1 : 0;
+  return B200VQA_OK;
+}
+
+extern "C" int b200vqa_profile_read_flow(b200vqa_t* h, double* ms_out, int64_t* launches, double* bytes) {
+  if (!h) return B200VQA_EINVAL;
+  VQA_CUDA(cudaSetDevice(h->device));
+  VQA_CUDA(cudaDeviceSynchronize());
+  double ms = 0.0;
+  for (auto& ev : h->prof_events_flow) {
+    float t = 0.f;
+    VQA_CUDA(cudaEventElapsedTime(&t, ev.first, ev.second));
+    ms += t;
+    h->prof_pool.push_back(ev);
+  }
+  if (ms_out) *ms_out = ms;
+  if (launches) *launches = (int64_t)h->prof_events_flow.size();
+  if (bytes) *bytes = h->prof_bytes_flow;
+  h->prof_events_flow.clear();
+  h->prof_bytes_flow = 0.0;
   return B200VQA_OK;
 }
 

@@ -35,7 +35,9 @@ struct b200vqa_ctx {
   int gemm_impl = 0;                       // 0 tcgen05, 1 SIMT check kernels
   int64_t launches = 0;
   int profiling = 0;
-  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;          // class 0: tcgen05 GEMM / conv launches
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events_flow;     // class 1: k4_flow_iter launches
+  double prof_bytes_flow = 0.0;                                          // algorithmic bytes of those launches
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_pool;
   double prof_flops = 0.0;
   std::map<std::pair<int, int>, b200vqa::ResizeTable> resize_tables;   // (in_size, filter)

@@ -678,7 +678,18 @@ extern "C" int b200vqa_farneback(b200vqa_t* h, const uint8_t* gray0, const uint8
     float* fout = nullptr;
     for (int it = 0; it < 3; ++it) {
       fout = (last && it == 2) ? flow : (fin == flowA ? flowB : flowA);
+      std::pair<cudaEvent_t, cudaEvent_t> ev{};
+      if (h->profiling) {
+        if (!h->prof_pool.empty()) { ev = h->prof_pool.back(); h->prof_pool.pop_back(); }
+        else { VQA_CUDA(cudaEventCreate(&ev.first)); VQA_CUDA(cudaEventCreate(&ev.second)); }
+        VQA_CUDA(cudaEventRecord(ev.first, st));
+      }
       k4_flow_iter<<<gbox, 256, BX_SMEM, st>>>(RA0, RB0, RA1, RB1, fin, L.h, L.w, fout);
+      if (h->profiling) {
+        VQA_CUDA(cudaEventRecord(ev.second, st));
+        h->prof_events_flow.push_back(ev);
+        h->prof_bytes_flow += 56.0 * (double)B * lp;       // R0 20 + R1 20 + flow 8 read, flow 8 written, per pixel
+      }
       VQA_LAUNCH_CHECK();
       fin = fout;
     }

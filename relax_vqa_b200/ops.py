@@ -51,6 +51,12 @@ class Context:
         check(self.lib.b200vqa_profile_read(self.h, C.byref(ms), C.byref(n), C.byref(fl)), "profile_read")
         return ms.value, n.value, fl.value
 
+    def profile_read_flow(self):
+        """-> (ms spent in k4_flow_iter launches, launches, algorithmic bytes) since the last read."""
+        ms, n, by = C.c_double(), C.c_int64(), C.c_double()
+        check(self.lib.b200vqa_profile_read_flow(self.h, C.byref(ms), C.byref(n), C.byref(by)), "profile_read_flow")
+        return ms.value, n.value, by.value
+
     def set_gemm_impl(self, impl):
         check(self.lib.b200vqa_set_gemm_impl(self.h, int(impl)), "set_gemm_impl")
 

@@ -252,38 +252,31 @@ __device__ __forceinline__ float border_w(int i, int n) {
   return s;
 }
 
-// 56 x 32 outputs per block, 2 x 2 blocks per thread-block cluster.  A block computes the structure tensor only on
-// its core plus the halo strips that face OUT of the cluster (a 63 x 39 rectangle = two warp-wide passes per row) and
-// reads the strips that face a cluster mate from that mate's shared memory (DSMEM): 1.39 computed pixels per output
-// instead of 1.92 for an isolated 48 x 32 tile.
-constexpr int BX_TX = 56, BX_TY = 32, BX_M = 7, BX_W = BX_TX + 2 * BX_M, BX_H = BX_TY + 2 * BX_M, BX_LD = 71;   // 70, 46
-constexpr int BX_RW = BX_TX + BX_M, BX_RH = BX_TY + BX_M;                                                      // 63, 39
+// 48 x 32 outputs per block: the 62-pixel halo row is covered by exactly two warp-wide passes (64 lanes)
+constexpr int BX_TX = 48, BX_TY = 32, BX_M = 7, BX_W = BX_TX + 2 * BX_M, BX_H = BX_TY + 2 * BX_M, BX_LD = 65;   // 62, 46
 constexpr int BX_SEG = BX_TX / 8;                                                                            // columns per warp in phase C
 constexpr int BX_SMEM = 5 * BX_H * BX_LD * 4;
-__global__ void __cluster_dims__(2, 2, 1) __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(256, 3)
 k4_flow_iter(const float4* __restrict__ RA0, const float* __restrict__ RB0, const float4* __restrict__ RA1,
              const float* __restrict__ RB1, const float* __restrict__ flow_in, int h, int w, float* __restrict__ flow_out) {
-  extern __shared__ float Ms[];                      // [5][46][71]; rows 0..31 become the vertical sums in place
+  extern __shared__ float Ms[];                      // [5][46][65]; rows 0..31 become the vertical sums in place
   const int x0 = blockIdx.x * BX_TX, y0 = blockIdx.y * BX_TY;
   const size_t plane = (size_t)h * w, zo = (size_t)blockIdx.z * plane;
   const float2* fin = reinterpret_cast<const float2*>(flow_in) + zo;
   const int tid = threadIdx.x, wrp = tid >> 5, lane = tid & 31;
   // phase A: structure-tensor entries at the (replicate-clamped) halo pixels; one warp per halo row, two pixels
   // per lane processed together so that their dependent gathers (flow -> address -> R1 taps) overlap.  Branch-free:
-  // out-of-image taps are clamped and blended out, lane 63 of the second pass recomputes the last column.
+  // out-of-image taps are clamped and blended out, lanes 62/63 of the second pass recompute column 61.
   const float4* ra0 = RA0 + zo; const float* rb0 = RB0 + zo;
   const float4* ra1 = RA1 + zo; const float* rb1 = RB1 + zo;
-  const int cx = blockIdx.x & 1, cy = blockIdx.y & 1;            // position inside the 2 x 2 cluster
-  const int rx0 = cx ? BX_M : 0, ry0 = cy ? BX_M : 0;            // origin of the rectangle this block computes
-  for (int tr = wrp; tr < BX_RH; tr += 8) {
-    const int ty = ry0 + tr;
+  for (int ty = wrp; ty < BX_H; ty += 8) {
     const int y = min(max(y0 + ty - BX_M, 0), h - 1);
     const int yo = y * w;
     int xs[2], txs[2];
     float2 d[2]; float4 c0[2]; float c0xy[2];
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
-      txs[u] = rx0 + min(lane + 32 * u, BX_RW - 1);
+      txs[u] = min(lane + 32 * u, BX_W - 1);
       xs[u] = min(max(x0 + txs[u] - BX_M, 0), w - 1);
       const int o = yo + xs[u];
       d[u] = fin[o]; c0[u] = ra0[o]; c0xy[u] = rb0[o];
@@ -333,39 +326,7 @@ k4_flow_iter(const float4* __restrict__ RA0, const float* __restrict__ RB0, cons
       m[4 * BX_H * BX_LD] = r6 * r2 + r5 * r3;
     }
   }
-  // cluster barrier (release/acquire): every mate's rectangle is complete and visible
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-  // phase A': pull the halo strips that lie in a mate's rectangle.  Strip towards the x-mate: 7 columns x 46 rows;
-  // towards the y-mate (and the diagonal mate for its corner): 7 rows x 63 columns.
-  {
-    const uint32_t my = (uint32_t)__cvta_generic_to_shared(Ms);
-    uint32_t base[4];
-#pragma unroll
-    for (int r = 0; r < 4; ++r) asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(base[r]) : "r"(my), "r"(r));
-    const int sx0 = cx ? 0 : BX_RW, sy0 = cy ? 0 : BX_RH;        // first column / row of the missing strips
-    const int n_x = BX_M * BX_H, n_y = BX_M * BX_RW;             // 322 + 441 pixels
-    for (int i = tid; i < n_x + n_y; i += 256) {
-      int tx, ty;
-      if (i < n_x) { ty = i / BX_M; tx = sx0 + (i - ty * BX_M); }
-      else { const int k = i - n_x; const int rr = k / BX_RW; ty = sy0 + rr; tx = rx0 + (k - rr * BX_RW); }
-      // owner = the mate whose rectangle holds this pixel; coordinates in the owner's tile shift by one tile size
-      const int ox = (cx ? tx < BX_M : tx >= BX_RW) ? (cx ^ 1) : cx;
-      const int oy = (cy ? ty < BX_M : ty >= BX_RH) ? (cy ^ 1) : cy;
-      const int otx = tx + (ox != cx ? (cx ? BX_TX : -BX_TX) : 0), oty = ty + (oy != cy ? (cy ? BX_TY : -BX_TY) : 0);
-      const uint32_t src = base[ox + 2 * oy] + (uint32_t)((oty * BX_LD + otx) * 4);
-      float* dst = Ms + ty * BX_LD + tx;
-#pragma unroll
-      for (int c = 0; c < 5; ++c) {
-        float v;
-        asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(src + (uint32_t)(c * BX_H * BX_LD * 4)));
-        dst[c * BX_H * BX_LD] = v;
-      }
-    }
-  }
-  // second cluster barrier: no mate still reads this block's rectangle once phase B starts overwriting it
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+  __syncthreads();
   // phase B: vertical sliding sums, in place (f32; the walk is 32 rows, error ~ a direct 15-tap sum).
   // The sum for output row r is written over input row r one step late, after that row's last use.
   for (int task = tid; task < 5 * BX_W; task += 256) {
@@ -713,7 +674,7 @@ extern "C" int b200vqa_farneback(b200vqa_t* h, const uint8_t* gray0, const uint8
       k4_flow_upsample<<<dim3(cdiv(L.w, 256), L.h, B), 256, 0, st>>>(prev, ph, pw, L.h, L.w, (double)pw / L.w, (double)ph / L.h, fin);
       VQA_LAUNCH_CHECK();
     }
-    const dim3 gbox((cdiv(L.w, BX_TX) + 1) & ~1, (cdiv(L.h, BX_TY) + 1) & ~1, B);      // whole 2 x 2 clusters
+    const dim3 gbox(cdiv(L.w, BX_TX), cdiv(L.h, BX_TY), B);
     float* fout = nullptr;
     for (int it = 0; it < 3; ++it) {
       fout = (last && it == 2) ? flow : (fin == flowA ? flowB : flowA);

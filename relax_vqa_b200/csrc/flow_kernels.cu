@@ -152,11 +152,23 @@ k4_polyexp(const float* __restrict__ I, const uint8_t* __restrict__ gray0, const
     const uint8_t* g = (z < B ? gray0 + (size_t)z * h * w : gray1 + (size_t)(z - B) * h * w);
     // row-filtered gray at raw coordinates (y0-6+ty, x0-5+tx): rows 0..27, cols 0..73
     const bool interior = x0 - PE_N - 1 >= 0 && x0 + PE_TW + PE_N + 1 <= w && y0 - 6 >= 0 && y0 + PE_TH + 6 <= h;
-    if (interior) {                                                    // no clamping / reflection needed
+    if (interior && (w & 3) == 0 && (((uintptr_t)g & 3) == 0)) {      // no clamping / reflection needed
+      // stage the 28 x 80-byte gray window with independent 32-bit loads (all in flight at once), then filter from smem
+      __shared__ uint32_t graw[PE_LH + 2][20];
+      const uint8_t* g0 = g + (size_t)(y0 - 6) * w + (x0 - 8);         // x0 is a multiple of 64 -> 4-byte aligned
+#pragma unroll
+      for (int it = 0; it < 3; ++it) {
+        const int i = tid + it * 256;
+        if (i < (PE_LH + 2) * 20) { const int r = i / 20, c = i - r * 20; graw[r][c] = __ldg(reinterpret_cast<const uint32_t*>(g0 + (size_t)r * w) + c); }
+      }
+      __syncthreads();
       for (int ty = wrp; ty < PE_LH + 2; ty += 8) {
-        const uint8_t* grow = g + (size_t)(y0 - 6 + ty) * w + (x0 - PE_N - 1);
-        for (int tx = lane; tx < PE_LW; tx += 32)
-          hrow[ty][tx] = (int)grow[tx] + 2 * (int)grow[tx + 1] + (int)grow[tx + 2];
+        const uint8_t* grow = reinterpret_cast<const uint8_t*>(graw[ty]) + 2;      // byte of global column x0 - 6
+#pragma unroll
+        for (int it = 0; it < 3; ++it) {
+          const int tx = lane + 32 * it;
+          if (tx < PE_LW) hrow[ty][tx] = (int)grow[tx] + 2 * (int)grow[tx + 1] + (int)grow[tx + 2];
+        }
       }
     } else {
       for (int ty = wrp; ty < PE_LH + 2; ty += 8) {
@@ -176,9 +188,13 @@ k4_polyexp(const float* __restrict__ I, const uint8_t* __restrict__ gray0, const
     }
   } else {
     const float* img = I + (size_t)z * h * w;
-    for (int ty = wrp; ty < PE_LH; ty += 8) {
-      const float* irow = img + (size_t)min(max(y0 + ty - PE_N, 0), h - 1) * w;
-      for (int tx = lane; tx < PE_LW; tx += 32) tile[ty][tx] = irow[min(max(x0 + tx - PE_N, 0), w - 1)];
+#pragma unroll
+    for (int it = 0; it < (PE_LH * PE_LW + 255) / 256; ++it) {        // independent loads, all in flight at once
+      const int i = tid + it * 256;
+      if (i < PE_LH * PE_LW) {
+        const int ty = i / PE_LW, tx = i - ty * PE_LW;
+        tile[ty][tx] = img[(size_t)min(max(y0 + ty - PE_N, 0), h - 1) * w + min(max(x0 + tx - PE_N, 0), w - 1)];
+      }
     }
   }
   __syncthreads();

@@ -334,7 +334,8 @@ extern "C" int b200vqa_resnet50_features(b200vqa_t* h, const uint8_t* img, int B
   cudaStream_t st = as_stream(stream);
   const ResNetWeights& rw = *h->resnet;
   const int CH = 128;                                  // images per pass (bounds the workspace; fills the 7x7 layers' tile grid)
-  const int nb = B < CH ? B : CH;
+  const int passes = cdiv(B, CH);
+  const int nb = cdiv(B, passes);                      // balanced passes: no tiny, latency-bound remainder pass
   // workspace carve-up (bytes), all fp16 NHWC unless noted
   const size_t sz_col = (size_t)nb * 12544 * 192 * 2, sz_c1 = (size_t)nb * 12544 * 64 * 2, sz_big = (size_t)nb * 3136 * 256 * 2;
   const size_t sz_mid = (size_t)nb * 3136 * 128 * 2;

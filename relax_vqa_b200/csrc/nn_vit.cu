@@ -391,7 +391,8 @@ extern "C" int b200vqa_vitb16_features(b200vqa_t* h, const uint8_t* img, int B, 
   // images per pass: 127 x 197 tokens = 98 row-tile pairs -> the 3 / 9 / 12 column tiles of the ViT linears fill the
   // 74 SM pairs in whole waves (294, 882, 1176 tiles), avoiding a nearly empty trailing wave
   const int CH = 127;
-  const int nb = B < CH ? B : CH;
+  const int passes = cdiv(B, CH);
+  const int nb = cdiv(B, passes);                      // balanced passes
   const size_t M = (size_t)nb * VT;
   size_t off = 0;
   auto carve = [&](size_t bytes) { size_t o = off; off += (bytes + 1023) / 1024 * 1024; return o; };

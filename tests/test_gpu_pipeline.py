@@ -200,3 +200,29 @@ def test_odd_resolution_clip_vs_oracle(engine, hw):
     got = engine.extract([clip])[0].cpu().numpy()
     e = seg_err(got, ref[None], VEC_SEGS)
     assert max(e) <= 1e-2, e
+
+
+def test_srcc_and_mos_parity_over_several_videos(golden_dir):
+    """north_star acceptance: |dMOS| <= 0.01 and SRCC >= 0.999 against the reference path's predictions, here the CPU
+    oracle (itself pinned to the unmodified reference) on 8 distinct small clips with shared seeded weights."""
+    import scipy.stats
+    from relax_vqa_b200.engine import Clip, Engine
+    s = np.load(os.path.join(golden_dir, "konvid_1k_scaler_imputer.npz"))
+    rsd, vsd = weights.seeded_resnet50_state_dict(1234), weights.seeded_vitb16_state_dict(4321)
+    hsd = weights.seeded_head_state_dict(99, swa_format=True)
+    eng = Engine(0, rsd, vsd, hsd, s["imputer_mean"], s["scale"], s["minv"])
+    clips, ref = [], []
+    for i, hw in enumerate([(144, 256), (160, 240), (144, 256), (176, 208), (144, 256), (128, 320), (160, 240), (144, 256)]):
+        fr, nx = synth.make_clip(500 + i, hw[0], hw[1], 2)
+        fr = np.clip(fr.astype(np.int32) * (0.5 + 0.12 * i), 0, 255).astype(np.uint8)      # spread the content / scores
+        nx = np.clip(nx.astype(np.int32) * (0.5 + 0.12 * i), 0, 255).astype(np.uint8)
+        clips.append(Clip(torch.from_numpy(fr).cuda(), torch.from_numpy(nx).cuda()))
+        vec = P.video_vector(P.video_feature_blocks(fr, nx, rsd, vsd))
+        ref.append(P.predict(vec, weights.fix_state_dict(hsd), s["imputer_mean"], s["scale"], s["minv"], "konvid_1k"))
+    _, score = eng.predict(clips, "konvid_1k")
+    got = score.cpu().numpy()
+    ref = np.array(ref)
+    print("MOS gpu", np.round(got, 4), "oracle", np.round(ref, 4))
+    assert np.abs(got - ref).max() <= 0.01
+    assert scipy.stats.spearmanr(got, ref).correlation >= 0.999
+    eng.close()

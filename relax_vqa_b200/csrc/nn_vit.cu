@@ -114,18 +114,32 @@ k10_attention(const __half* __restrict__ qkv, __half* __restrict__ out, float sc
   const int hh = blockIdx.x, b = blockIdx.y;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const __half* base = qkv + (size_t)b * VT * (3 * VD) + hh * VHD;
-  for (int i = tid; i < AT_NP * 8; i += AT_WARPS * 32) {
-    const int row = i >> 3, ch = i & 7;
-    uint4 kv = make_uint4(0, 0, 0, 0), vv = kv;
-    if (row < VT) {
-      kv = *reinterpret_cast<const uint4*>(base + (size_t)row * (3 * VD) + VD + ch * 8);
-      vv = *reinterpret_cast<const uint4*>(base + (size_t)row * (3 * VD) + 2 * VD + ch * 8);
+  {
+    constexpr int kIters = (AT_NP * 8 + AT_WARPS * 32 - 1) / (AT_WARPS * 32);      // 7: all loads issued before the first store
+    uint4 kv[kIters], vv[kIters];
+#pragma unroll
+    for (int it = 0; it < kIters; ++it) {
+      const int i = tid + it * AT_WARPS * 32;
+      const int row = i >> 3, ch = i & 7;
+      kv[it] = make_uint4(0, 0, 0, 0); vv[it] = kv[it];
+      if (i < AT_NP * 8 && row < VT) {
+        kv[it] = __ldg(reinterpret_cast<const uint4*>(base + (size_t)row * (3 * VD) + VD + ch * 8));
+        vv[it] = __ldg(reinterpret_cast<const uint4*>(base + (size_t)row * (3 * VD) + 2 * VD + ch * 8));
+      }
     }
-    *reinterpret_cast<uint4*>(&sK[row][ch * 8]) = kv;
-    *reinterpret_cast<uint4*>(&sV[row][ch * 8]) = vv;
+#pragma unroll
+    for (int it = 0; it < kIters; ++it) {
+      const int i = tid + it * AT_WARPS * 32;
+      if (i < AT_NP * 8) {
+        const int row = i >> 3, ch = i & 7;
+        *reinterpret_cast<uint4*>(&sK[row][ch * 8]) = kv[it];
+        *reinterpret_cast<uint4*>(&sV[row][ch * 8]) = vv[it];
+      }
+    }
   }
   __syncthreads();
   const int g = lane >> 2, t4 = lane & 3;
+  const float sl2 = scale * 1.4426950408889634f;             // scale * log2(e)
   for (int qb = warp; qb < AT_NP / 16; qb += AT_WARPS) {
     for (int i = lane; i < 16 * 8; i += 32) {
       const int r = i >> 3, ch = i & 7, row = qb * 16 + r;
@@ -168,7 +182,7 @@ k10_attention(const __half* __restrict__ qkv, __half* __restrict__ out, float sc
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const int col = key0 + nt * 8 + t4 * 2 + (e & 1);
-          s[nt][e] = (nt < ntn && col < VT) ? s[nt][e] * scale : -INFINITY;
+          s[nt][e] = (nt < ntn && col < VT) ? s[nt][e] : -INFINITY;      // raw scores; scale > 0 is folded into the exponent
         }
         hm0 = fmaxf(hm0, fmaxf(s[nt][0], s[nt][1]));
         hm1 = fmaxf(hm1, fmaxf(s[nt][2], s[nt][3]));
@@ -176,16 +190,17 @@ k10_attention(const __half* __restrict__ qkv, __half* __restrict__ out, float sc
       hm0 = fmaxf(hm0, __shfl_xor_sync(0xffffffffu, hm0, 1)); hm0 = fmaxf(hm0, __shfl_xor_sync(0xffffffffu, hm0, 2));
       hm1 = fmaxf(hm1, __shfl_xor_sync(0xffffffffu, hm1, 1)); hm1 = fmaxf(hm1, __shfl_xor_sync(0xffffffffu, hm1, 2));
       const float n0 = fmaxf(m0, hm0), n1 = fmaxf(m1, hm1);
-      const float c0 = __expf(m0 - n0), c1 = __expf(m1 - n1);     // rescale of the running sums (exp(-inf) = 0 on the first half)
+      const float c0 = exp2f((m0 - n0) * sl2), c1 = exp2f((m1 - n1) * sl2);     // rescale of the running sums (0 on the first half)
       m0 = n0; m1 = n1;
+      const float mk0 = m0 * sl2, mk1 = m1 * sl2;
       l0 *= c0; l1 *= c1;
 #pragma unroll
       for (int i = 0; i < 8; ++i) { o[i][0] *= c0; o[i][1] *= c0; o[i][2] *= c1; o[i][3] *= c1; }
       float h0 = 0.f, h1 = 0.f;
 #pragma unroll
       for (int nt = 0; nt < NT_MAX; ++nt) {
-        s[nt][0] = __expf(s[nt][0] - m0); s[nt][1] = __expf(s[nt][1] - m0);
-        s[nt][2] = __expf(s[nt][2] - m1); s[nt][3] = __expf(s[nt][3] - m1);
+        s[nt][0] = exp2f(fmaf(s[nt][0], sl2, -mk0)); s[nt][1] = exp2f(fmaf(s[nt][1], sl2, -mk0));   // exp(scale * (s - m))
+        s[nt][2] = exp2f(fmaf(s[nt][2], sl2, -mk1)); s[nt][3] = exp2f(fmaf(s[nt][3], sl2, -mk1));
         h0 += s[nt][0] + s[nt][1]; h1 += s[nt][2] + s[nt][3];
       }
       l0 += h0; l1 += h1;                                          // per-thread partial row sums; reduced across the quad at the end

@@ -25,7 +25,7 @@ __device__ __forceinline__ int reflect101(int i, int n) {
 // INTER_LINEAR at the level's pixel centres.  One block = 32 x 8 outputs; the source window is staged in
 // shared memory (uint8), blurred horizontally only at the <= 64 columns the bilinear taps need (f32, smem),
 // then blurred vertically at the <= 2 rows each output needs.  Row filter before column filter, like OpenCV.
-constexpr int PY_TX = 32, PY_TY = 8;
+constexpr int PY_TX = 32;
 __device__ __forceinline__ void lin_split(int d, double scale, int n_in, bool same, int& i0, int& i1, float& a) {
   if (same) { i0 = i1 = d; a = 0.f; return; }
   const double s = (d + 0.5) * scale - 0.5;
@@ -37,12 +37,17 @@ __device__ __forceinline__ void lin_split(int d, double scale, int n_in, bool sa
 }
 
 // KS = Gaussian kernel size known at compile time (3, 9, 19 for pyramid levels 1..3) so the tap loops unroll with
-// the taps in registers; KS = 0 is the generic run-time-size fallback (unusual resolutions).
-template <int KS>
+// the taps in registers; KS = 0 is the generic run-time-size fallback (unusual resolutions).  TY = output rows per
+// block (32 / 16 / 8 for the three levels: the finer the level, the smaller its source window per output, so more
+// outputs per block amortise the per-block setup).  The bilinear source coordinates of the tile's 32 columns and TY
+// rows are computed once (in double, like cv::resize) into shared tables.
+template <int KS, int TY>
 __global__ void __launch_bounds__(256)
 k4_pyr_level(const uint8_t* __restrict__ gray0, const uint8_t* __restrict__ gray1, int B, int H, int W, Taps taps, int h, int w,
              double sx, double sy, float* __restrict__ out) {
   extern __shared__ __align__(16) uint8_t py_smem[];
+  __shared__ int s_xa[PY_TX], s_xb[PY_TX], s_ya[TY], s_yb[TY];
+  __shared__ float s_ax[PY_TX], s_ay[TY];
   const int ks = KS ? KS : taps.ksize;
   const int r = ks >> 1;
   float tp[KS ? KS : 1];
@@ -53,13 +58,14 @@ k4_pyr_level(const uint8_t* __restrict__ gray0, const uint8_t* __restrict__ gray
   const bool same = (h == H && w == W);
   const int z = blockIdx.z;
   const uint8_t* img = (z < B ? gray0 + (size_t)z * H * W : gray1 + (size_t)(z - B) * H * W);
-  const int xo0 = blockIdx.x * PY_TX, yo0 = blockIdx.y * PY_TY;
-  const int xo_last = min(xo0 + PY_TX, w) - 1, yo_last = min(yo0 + PY_TY, h) - 1;
-  int i0, i1; float a;
-  lin_split(xo0, sx, W, same, i0, i1, a);      int x_lo = i0 - r;
-  lin_split(xo_last, sx, W, same, i0, i1, a);  const int x_hi = i1 + r;
-  lin_split(yo0, sy, H, same, i0, i1, a);      const int y_lo = i0 - r;
-  lin_split(yo_last, sy, H, same, i0, i1, a);  const int y_hi = i1 + r;
+  const int xo0 = blockIdx.x * PY_TX, yo0 = blockIdx.y * TY;
+  const int tid = threadIdx.x;
+  const int wrp = tid >> 5, lane = tid & 31;
+  if (tid < PY_TX) { int i0, i1; float a; lin_split(min(xo0 + tid, w - 1), sx, W, same, i0, i1, a); s_xa[tid] = i0; s_xb[tid] = i1; s_ax[tid] = a; }
+  else if (tid < PY_TX + TY) { const int j = tid - PY_TX; int i0, i1; float a; lin_split(min(yo0 + j, h - 1), sy, H, same, i0, i1, a); s_ya[j] = i0; s_yb[j] = i1; s_ay[j] = a; }
+  __syncthreads();
+  int x_lo = s_xa[0] - r;
+  const int x_hi = s_xb[PY_TX - 1] + r, y_lo = s_ya[0] - r, y_hi = s_yb[TY - 1] + r;
   // interior tiles whose rows are 4-byte addressable are staged with 32-bit loads (window start aligned down)
   const bool vec = (W & 3) == 0 && (((uintptr_t)img & 3) == 0) && y_lo >= 0 && y_hi < H && (x_lo & ~3) >= 0 &&
                    (x_lo & ~3) + ((x_hi - (x_lo & ~3) + 4) & ~3) <= W;
@@ -68,13 +74,11 @@ k4_pyr_level(const uint8_t* __restrict__ gray0, const uint8_t* __restrict__ gray
   const int sw_p = (sw + 3) & ~3;
   uint8_t* src = py_smem;                                         // [sh][sw_p] uint8
   float* hs = reinterpret_cast<float*>(py_smem + (((size_t)sh * sw_p + 15) & ~(size_t)15));   // [sh][2*PY_TX] f32
-  const int tid = threadIdx.x;
-  const int wrp = tid >> 5, lane = tid & 31;
   if (vec) {
-    for (int ty = wrp; ty < sh; ty += 8) {                         // one warp per source row
-      const uint32_t* grow = reinterpret_cast<const uint32_t*>(img + (size_t)(y_lo + ty) * W + x_lo);
-      uint32_t* drow = reinterpret_cast<uint32_t*>(src + ty * sw_p);
-      for (int tx = lane; tx < (sw_p >> 2); tx += 32) drow[tx] = __ldg(grow + tx);
+    const int wpr = sw_p >> 2;                                     // 32-bit words per row
+    for (int i = tid; i < sh * wpr; i += 256) {
+      const int ty = i / wpr, tx = i - ty * wpr;
+      reinterpret_cast<uint32_t*>(src + ty * sw_p)[tx] = __ldg(reinterpret_cast<const uint32_t*>(img + (size_t)(y_lo + ty) * W + x_lo) + tx);
     }
   } else {
     for (int ty = wrp; ty < sh; ty += 8) {
@@ -88,9 +92,7 @@ k4_pyr_level(const uint8_t* __restrict__ gray0, const uint8_t* __restrict__ gray
 #pragma unroll
   for (int u = 0; u < 2; ++u) {
     const int slot = lane + 32 * u;
-    const int xo = min(xo0 + (slot >> 1), w - 1);
-    lin_split(xo, sx, W, same, i0, i1, a);
-    xc2[u] = ((slot & 1) ? i1 : i0) - r - x_lo;                    // window start inside the tile
+    xc2[u] = ((slot & 1) ? s_xb[slot >> 1] : s_xa[slot >> 1]) - r - x_lo;      // window start inside the tile
   }
   for (int ty = wrp; ty < sh; ty += 8) {
 #pragma unroll
@@ -107,29 +109,31 @@ k4_pyr_level(const uint8_t* __restrict__ gray0, const uint8_t* __restrict__ gray
     }
   }
   __syncthreads();
-  const int tx = tid & (PY_TX - 1), ty = tid / PY_TX;
-  const int xo = xo0 + tx, yo = yo0 + ty;
-  if (xo < w && yo < h) {
-    float ax, ay; int xa, xb, ya, yb;
-    lin_split(xo, sx, W, same, xa, xb, ax);
-    lin_split(yo, sy, H, same, ya, yb, ay);
-    const float* c0 = hs + (size_t)(ya - r - y_lo) * (2 * PY_TX) + 2 * tx;
-    const float* c1 = hs + (size_t)(yb - r - y_lo) * (2 * PY_TX) + 2 * tx;
-    float b00 = 0.f, b01 = 0.f, b10 = 0.f, b11 = 0.f;
-    if (KS) {
+  const int tx = lane;
+  const int xo = xo0 + tx;
+  const float ax = s_ax[tx];
+  for (int ty = wrp; ty < TY; ty += 8) {
+    const int yo = yo0 + ty;
+    if (xo < w && yo < h) {
+      const float ay = s_ay[ty];
+      const float* c0 = hs + (size_t)(s_ya[ty] - r - y_lo) * (2 * PY_TX) + 2 * tx;
+      const float* c1 = hs + (size_t)(s_yb[ty] - r - y_lo) * (2 * PY_TX) + 2 * tx;
+      float b00 = 0.f, b01 = 0.f, b10 = 0.f, b11 = 0.f;
+      if (KS) {
 #pragma unroll
-      for (int k = 0; k < (KS ? KS : 1); ++k) {
-        const float2 p0 = *reinterpret_cast<const float2*>(c0 + k * 2 * PY_TX), p1 = *reinterpret_cast<const float2*>(c1 + k * 2 * PY_TX);
-        b00 += tp[k] * p0.x; b01 += tp[k] * p0.y; b10 += tp[k] * p1.x; b11 += tp[k] * p1.y;
+        for (int k = 0; k < (KS ? KS : 1); ++k) {
+          const float2 p0 = *reinterpret_cast<const float2*>(c0 + k * 2 * PY_TX), p1 = *reinterpret_cast<const float2*>(c1 + k * 2 * PY_TX);
+          b00 += tp[k] * p0.x; b01 += tp[k] * p0.y; b10 += tp[k] * p1.x; b11 += tp[k] * p1.y;
+        }
+      } else {
+        for (int k = 0; k < ks; ++k) {
+          const float t = taps.t[k];
+          b00 += t * c0[k * 2 * PY_TX]; b01 += t * c0[k * 2 * PY_TX + 1]; b10 += t * c1[k * 2 * PY_TX]; b11 += t * c1[k * 2 * PY_TX + 1];
+        }
       }
-    } else {
-      for (int k = 0; k < ks; ++k) {
-        const float t = taps.t[k];
-        b00 += t * c0[k * 2 * PY_TX]; b01 += t * c0[k * 2 * PY_TX + 1]; b10 += t * c1[k * 2 * PY_TX]; b11 += t * c1[k * 2 * PY_TX + 1];
-      }
+      const float top = b00 * (1.f - ax) + b01 * ax, bot = b10 * (1.f - ax) + b11 * ax;
+      out[((size_t)z * h + yo) * w + xo] = top * (1.f - ay) + bot * ay;
     }
-    const float top = b00 * (1.f - ax) + b01 * ax, bot = b10 * (1.f - ax) + b11 * ax;
-    out[((size_t)z * h + yo) * w + xo] = top * (1.f - ay) + bot * ay;
   }
 }
 
@@ -646,10 +650,10 @@ extern "C" int b200vqa_farneback(b200vqa_t* h, const uint8_t* gray0, const uint8
   static bool attr_done = false;
   if (!attr_done) {
     VQA_CUDA(cudaFuncSetAttribute(k4_flow_iter, cudaFuncAttributeMaxDynamicSharedMemorySize, BX_SMEM));
-    VQA_CUDA(cudaFuncSetAttribute(k4_pyr_level<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    VQA_CUDA(cudaFuncSetAttribute(k4_pyr_level<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    VQA_CUDA(cudaFuncSetAttribute(k4_pyr_level<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    VQA_CUDA(cudaFuncSetAttribute(k4_pyr_level<19>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    VQA_CUDA(cudaFuncSetAttribute(k4_pyr_level<0, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    VQA_CUDA(cudaFuncSetAttribute(k4_pyr_level<3, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    VQA_CUDA(cudaFuncSetAttribute(k4_pyr_level<9, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    VQA_CUDA(cudaFuncSetAttribute(k4_pyr_level<19, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     attr_done = true;
   }
   float* prev = nullptr;         // flow of the previous (coarser) level
@@ -668,14 +672,15 @@ extern "C" int b200vqa_farneback(b200vqa_t* h, const uint8_t* gray0, const uint8
     } else {
       const double sx = (double)W / L.w, sy = (double)H / L.h;
       // shared-memory window: uint8 source tile + f32 horizontally blurred columns
-      const int sw = (int)(PY_TX * sx) + L.ksize + 8, sh = (int)(PY_TY * sy) + L.ksize + 4;
+      const int TY = L.ksize == 3 ? 32 : (L.ksize == 9 ? 16 : 8);
+      const int sw = (int)(PY_TX * sx) + L.ksize + 8, sh = (int)(TY * sy) + L.ksize + 4;
       const size_t smem = (((size_t)sh * ((sw + 3) & ~3) + 15) & ~(size_t)15) + (size_t)sh * 2 * PY_TX * sizeof(float);
       if (smem > 100 * 1024) return B200VQA_EINVAL;
-      const dim3 gpyr(cdiv(L.w, PY_TX), cdiv(L.h, PY_TY), 2 * B);
-      if (L.ksize == 3) k4_pyr_level<3><<<gpyr, 256, smem, st>>>(gray0, gray1, B, H, W, taps, L.h, L.w, sx, sy, I);
-      else if (L.ksize == 9) k4_pyr_level<9><<<gpyr, 256, smem, st>>>(gray0, gray1, B, H, W, taps, L.h, L.w, sx, sy, I);
-      else if (L.ksize == 19) k4_pyr_level<19><<<gpyr, 256, smem, st>>>(gray0, gray1, B, H, W, taps, L.h, L.w, sx, sy, I);
-      else k4_pyr_level<0><<<gpyr, 256, smem, st>>>(gray0, gray1, B, H, W, taps, L.h, L.w, sx, sy, I);
+      const dim3 gpyr(cdiv(L.w, PY_TX), cdiv(L.h, TY), 2 * B);
+      if (L.ksize == 3) k4_pyr_level<3, 32><<<gpyr, 256, smem, st>>>(gray0, gray1, B, H, W, taps, L.h, L.w, sx, sy, I);
+      else if (L.ksize == 9) k4_pyr_level<9, 16><<<gpyr, 256, smem, st>>>(gray0, gray1, B, H, W, taps, L.h, L.w, sx, sy, I);
+      else if (L.ksize == 19) k4_pyr_level<19, 8><<<gpyr, 256, smem, st>>>(gray0, gray1, B, H, W, taps, L.h, L.w, sx, sy, I);
+      else k4_pyr_level<0, 8><<<gpyr, 256, smem, st>>>(gray0, gray1, B, H, W, taps, L.h, L.w, sx, sy, I);
       VQA_LAUNCH_CHECK();
       // I holds [2B][h][w]; expansion of images 0..B-1 then B..2B-1 (contiguous)
       k4_polyexp<false><<<dim3(cdiv(L.w, PE_TW), cdiv(L.h, PE_TH), 2 * B), 256, 0, st>>>(I, nullptr, nullptr, B, L.h, L.w, pc, RA, RB);

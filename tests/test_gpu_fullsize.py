@@ -1,6 +1,6 @@
 """Full-size (BASELINE.json configs: 1080p, 2160p) checks through the C ABI: exact integer stages vs the oracle,
 Farneback vs cv2 at 1080p, and size-independent properties at 2160p where the CPU oracle would take too long
-(identical frames -> zero residual / zero flow, translation of the pair -> translated positions, batch invariance,
+(identical frames -> zero residual, translation of the pair -> translated sums, batch invariance,
 host-buffer entry point == device-buffer entry point)."""
 import cv2
 import numpy as np
@@ -45,10 +45,11 @@ def test_2160p_properties(engine):
     H, W = 2160, 3840
     fr, nx = synth.make_clip(32, H, W, 1)
     f, n = _dev(fr), _dev(nx)
-    # identical frames: zero residual sums, zero flow, first 196 raster cells selected (all-ties rule)
+    # identical frames: zero residual sums and the first 196 raster cells selected (all-ties rule).  (The flow of
+    # identical frames is NOT zero in OpenCV's Farneback: pixels whose displaced position is the last row / column
+    # take the "outside" branch of UpdateMatrices - so the flow is compared with cv2 below instead.)
     same = engine.fragments(f, f, keep_intermediates=True)
     assert int(same["sums"].abs().sum()) == 0
-    assert float(same["flow"].abs().max()) == 0.0
     assert same["positions"][0].cpu().numpy().tolist() == [[i // 240, i % 240] for i in range(196)]
     # residual sums: checksum of checksums against numpy on the host (exact integers)
     r = ops.absdiff_patchsum(f, n)
@@ -57,6 +58,9 @@ def test_2160p_properties(engine):
     assert r["sums"].shape == (1, 135, 240)
     # translating both frames by a whole number of patches translates the selected positions
     out = engine.fragments(f, n, keep_intermediates=True)
+    ref = cv2.calcOpticalFlowFarneback(F.bgr2gray(fr[0]), F.bgr2gray(nx[0]), None, 0.5, 3, 15, 3, 5, 1.2, 0)      # ~4 s on the host
+    err = np.abs(out["flow"][0].cpu().numpy() - ref)
+    assert err.max() < 2e-3 and err.mean() < 2e-5, (err.max(), err.mean())
     fs, ns = torch.roll(f, shifts=(32, 48), dims=(1, 2)), torch.roll(n, shifts=(32, 48), dims=(1, 2))
     out_s = engine.fragments(fs, ns, keep_intermediates=True)
     sums, sums_s = out["sums"][0], out_s["sums"][0]

@@ -156,6 +156,9 @@ int b200vqa_set_gemm_impl(b200vqa_t* h, int impl);
  * b200vqa_profile_read synchronises, returns the summed device time (ms), the launch count and the
  * algorithmic FLOPs (2*M*N*K of the un-padded problems) since the last read, and resets them. */
 int b200vqa_set_profiling(b200vqa_t* h, int on);
+/* debug switch for the Farneback iteration (A/B measurements): 0 = streaming column-strip kernel with bilinear-tap
+ * reuse (default), 1 = the same without tap reuse, 2 = the 48 x 32 tile kernel */
+int b200vqa_set_flow_impl(b200vqa_t* h, int impl);
 int b200vqa_profile_read(b200vqa_t* h, double* gemm_ms, int64_t* gemm_launches, double* gemm_flops);
 /* same for the Farneback iteration kernel (k4_flow_iter): device ms, launches, algorithmic bytes (56 B per pixel) */
 int b200vqa_profile_read_flow(b200vqa_t* h, double* ms, int64_t* launches, double* bytes);

@@ -42,6 +42,7 @@ SIGNATURES = {
     "b200vqa_launch_count": (c_int64, [c_void_p]),
     "b200vqa_set_gemm_impl": (c_int, [c_void_p, c_int]),
     "b200vqa_set_profiling": (c_int, [c_void_p, c_int]),
+    "b200vqa_set_flow_impl": (c_int, [c_void_p, c_int]),
     "b200vqa_profile_read": (c_int, [c_void_p, C.POINTER(C.c_double), C.POINTER(c_int64), C.POINTER(C.c_double)]),
     "b200vqa_profile_read_flow": (c_int, [c_void_p, C.POINTER(C.c_double), C.POINTER(c_int64), C.POINTER(C.c_double)]),
 }

@@ -84,6 +84,12 @@ extern "C" int b200vqa_set_gemm_impl(b200vqa_t* h, int impl) {
   return B200VQA_OK;
 }
 
+extern "C" int b200vqa_set_flow_impl(b200vqa_t* h, int impl) {
+  if (!h || impl < 0 || impl > 2) return B200VQA_EINVAL;
+  h->flow_impl = impl;
+  return B200VQA_OK;
+}
+
 extern "C" int b200vqa_set_profiling(b200vqa_t* h, int on) {
   if (!h) return B200VQA_EINVAL;
   h->profiling = on ? 1 : 0;

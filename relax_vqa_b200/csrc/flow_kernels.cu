@@ -289,18 +289,27 @@ k4_flow_iter(const float4* __restrict__ RA0, const float* __restrict__ RB0, cons
   // out-of-image taps are clamped and blended out, lanes 62/63 of the second pass recompute column 61.
   const float4* ra0 = RA0 + zo; const float* rb0 = RB0 + zo;
   const float4* ra1 = RA1 + zo; const float* rb1 = RB1 + zo;
+  // the flow vector heads the dependent chain (flow -> tap address -> R1 taps): fetch it one row ahead
+  int xs[2], txs[2];
+  float2 dn[2];
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    txs[u] = min(lane + 32 * u, BX_W - 1);
+    xs[u] = min(max(x0 + txs[u] - BX_M, 0), w - 1);
+    dn[u] = fin[min(max(y0 + wrp - BX_M, 0), h - 1) * w + xs[u]];
+  }
   for (int ty = wrp; ty < BX_H; ty += 8) {
     const int y = min(max(y0 + ty - BX_M, 0), h - 1);
     const int yo = y * w;
-    int xs[2], txs[2];
+    const int yno = min(max(y0 + min(ty + 8, BX_H - 1) - BX_M, 0), h - 1) * w;
     float2 d[2]; float4 c0[2]; float c0xy[2];
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
-      txs[u] = min(lane + 32 * u, BX_W - 1);
-      xs[u] = min(max(x0 + txs[u] - BX_M, 0), w - 1);
       const int o = yo + xs[u];
-      d[u] = fin[o]; c0[u] = ra0[o]; c0xy[u] = rb0[o];
+      d[u] = dn[u]; c0[u] = ra0[o]; c0xy[u] = rb0[o];
     }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) dn[u] = fin[yno + xs[u]];
     float fx[2], fy[2], inside[2];
     float4 p00[2], p01[2], p10[2], p11[2]; float s00[2], s01[2], s10[2], s11[2];
 #pragma unroll
@@ -397,6 +406,177 @@ k4_flow_iter(const float4* __restrict__ RA0, const float* __restrict__ RB0, cons
           g[c] += row[15] - row[0];
         }
       }
+    }
+  }
+}
+
+// ---- (d+e), streaming form: one block owns a strip of MS_SX output columns (+ 8 halo columns each side, so the
+// strip starts on a 128-byte boundary of the float4 planes) and marches down a segment of rows, one thread per
+// column.  Per row a thread evaluates FarnebackUpdateMatrices at its pixel, slides the 15-row vertical box sum
+// (running sums in registers, the 15 previous rows of M in a shared-memory ring that only this thread touches), and
+// every MS_RB rows the block turns the vertical sums into 15-column sums with aligned 128-bit shared-memory windows
+// (4 adjacent outputs per thread) and solves.  Halo recompute: 256/240 columns x (rows + 14)/rows instead of the
+// 1.92x of the 48 x 32 tile kernel; moving down a column the upper two bilinear taps of a row are the lower two of
+// the previous row whenever the displacement is locally smooth, so they are reused from registers (kReuse).
+constexpr int MS_SX = 240, MS_HALO = 8, MS_NT = 256, MS_RB = 4;
+constexpr int MS_SMEM = (15 * 5 * MS_NT + MS_RB * 5 * MS_NT) * 4;          // ring + row-batch buffer = 97,280 B
+struct Tap2 { float4 a0, a1; float b0, b1; };                              // columns x1, x1 + 1 of one R1 row
+
+__device__ __forceinline__ Tap2 ld_tap2(const float4* __restrict__ ra, const float* __restrict__ rb, int q) {
+  Tap2 t; t.a0 = ra[q]; t.a1 = ra[q + 1]; t.b0 = rb[q]; t.b1 = rb[q + 1]; return t;
+}
+
+template <bool kReuse>
+__global__ void __launch_bounds__(MS_NT, 2)
+k4_flow_iter_march(const float4* __restrict__ RA0, const float* __restrict__ RB0, const float4* __restrict__ RA1,
+                   const float* __restrict__ RB1, const float* __restrict__ flow_in, int h, int w, int rows_per_seg,
+                   float* __restrict__ flow_out) {
+  extern __shared__ __align__(16) float ms_smem[];
+  float* ring = ms_smem;                               // [15][5][MS_NT]
+  float* hb = ms_smem + 15 * 5 * MS_NT;                // [MS_RB][5][MS_NT] vertical sums of the current row batch
+  const int tx = threadIdx.x;
+  const int x0 = blockIdx.x * MS_SX;
+  const int ya = blockIdx.y * rows_per_seg, yb = min(ya + rows_per_seg, h);
+  const size_t plane = (size_t)h * w, zo = (size_t)blockIdx.z * plane;
+  const float2* fin = reinterpret_cast<const float2*>(flow_in) + zo;
+  const float4* ra0 = RA0 + zo; const float* rb0 = RB0 + zo;
+  const float4* ra1 = RA1 + zo; const float* rb1 = RB1 + zo;
+  const int x = min(max(x0 - MS_HALO + tx, 0), w - 1);                      // replicate border: M at the clamped pixel
+  const bool xedge = (unsigned)(x - 5) >= (unsigned)(w - 10);
+  const float bwx = border_w(x, w);
+  const int nk = 14 + ((yb - ya + MS_RB - 1) & ~(MS_RB - 1));               // rows of M this block walks (even)
+  float vs[5], comp[5];
+#pragma unroll
+  for (int c = 0; c < 5; ++c) { vs[c] = 0.f; comp[c] = 0.f; }
+  int slot = 0;
+  float2 dn[2];
+#pragma unroll
+  for (int u = 0; u < 2; ++u) dn[u] = fin[min(max(ya - 7 + u, 0), h - 1) * w + x];
+  Tap2 pbot; pbot.a0 = pbot.a1 = make_float4(0.f, 0.f, 0.f, 0.f); pbot.b0 = pbot.b1 = 0.f;
+  int pq = -1;                                                              // address of the row held in pbot
+  for (int k = 0; k < nk; k += 2) {
+    int y[2], q[2]; float2 d[2]; float4 c0[2]; float c0xy[2]; float fx[2], fy[2]; bool in[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      y[u] = min(max(ya - 7 + k + u, 0), h - 1);
+      const int o = y[u] * w + x;
+      d[u] = dn[u]; c0[u] = ra0[o]; c0xy[u] = rb0[o];
+      const float gxf = (float)x + d[u].x, gyf = (float)y[u] + d[u].y;
+      const float flx = floorf(gxf), fly = floorf(gyf);
+      fx[u] = gxf - flx; fy[u] = gyf - fly;
+      const int x1 = (int)flx, y1 = (int)fly;
+      in[u] = (unsigned)x1 < (unsigned)(w - 1) && (unsigned)y1 < (unsigned)(h - 1);
+      q[u] = min(max(y1, 0), h - 2) * w + min(max(x1, 0), w - 2);
+    }
+    // lower tap rows are always fetched; upper rows only where they are not the previous row's lower taps
+    Tap2 bot[2], topl[2]; bool need[2];
+    need[0] = !kReuse || q[0] != pq;
+    need[1] = !kReuse || q[1] != q[0] + w;
+#pragma unroll
+    for (int u = 0; u < 2; ++u) bot[u] = ld_tap2(ra1, rb1, q[u] + w);
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      topl[u].a0 = topl[u].a1 = make_float4(0.f, 0.f, 0.f, 0.f); topl[u].b0 = topl[u].b1 = 0.f;
+      if (need[u]) topl[u] = ld_tap2(ra1, rb1, q[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) dn[u] = fin[min(max(ya - 7 + k + 2 + u, 0), h - 1) * w + x];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const Tap2 prev = u == 0 ? pbot : bot[0];
+      Tap2 top;
+      top.a0.x = need[u] ? topl[u].a0.x : prev.a0.x; top.a0.y = need[u] ? topl[u].a0.y : prev.a0.y;
+      top.a0.z = need[u] ? topl[u].a0.z : prev.a0.z; top.a0.w = need[u] ? topl[u].a0.w : prev.a0.w;
+      top.a1.x = need[u] ? topl[u].a1.x : prev.a1.x; top.a1.y = need[u] ? topl[u].a1.y : prev.a1.y;
+      top.a1.z = need[u] ? topl[u].a1.z : prev.a1.z; top.a1.w = need[u] ? topl[u].a1.w : prev.a1.w;
+      top.b0 = need[u] ? topl[u].b0 : prev.b0; top.b1 = need[u] ? topl[u].b1 : prev.b1;
+      const float dx = d[u].x, dy = d[u].y;
+      const float a00 = (1.f - fx[u]) * (1.f - fy[u]), a01 = fx[u] * (1.f - fy[u]), a10 = (1.f - fx[u]) * fy[u], a11 = fx[u] * fy[u];
+      float r2 = a00 * top.a0.x + a01 * top.a1.x + a10 * bot[u].a0.x + a11 * bot[u].a1.x;
+      float r3 = a00 * top.a0.y + a01 * top.a1.y + a10 * bot[u].a0.y + a11 * bot[u].a1.y;
+      float r4 = a00 * top.a0.z + a01 * top.a1.z + a10 * bot[u].a0.z + a11 * bot[u].a1.z;
+      float r5 = a00 * top.a0.w + a01 * top.a1.w + a10 * bot[u].a0.w + a11 * bot[u].a1.w;
+      float r6 = a00 * top.b0 + a01 * top.b1 + a10 * bot[u].b0 + a11 * bot[u].b1;
+      r2 = in[u] ? r2 : 0.f; r3 = in[u] ? r3 : 0.f;
+      r4 = in[u] ? (c0[u].z + r4) * 0.5f : c0[u].z;
+      r5 = in[u] ? (c0[u].w + r5) * 0.5f : c0[u].w;
+      r6 = in[u] ? (c0xy[u] + r6) * 0.25f : c0xy[u] * 0.5f;
+      r2 = (c0[u].x - r2) * 0.5f;
+      r3 = (c0[u].y - r3) * 0.5f;
+      r2 += r4 * dy + r6 * dx;
+      r3 += r6 * dy + r5 * dx;
+      if (xedge || (unsigned)(y[u] - 5) >= (unsigned)(h - 10)) {
+        const float s = border_w(y[u], h) * bwx;
+        r2 *= s; r3 *= s; r4 *= s; r5 *= s; r6 *= s;
+      }
+      float m[5];
+      m[0] = r4 * r4 + r6 * r6;
+      m[1] = (r4 + r5) * r6;
+      m[2] = r5 * r5 + r6 * r6;
+      m[3] = r4 * r2 + r6 * r3;
+      m[4] = r6 * r2 + r5 * r3;
+      // vertical running sums (compensated: a segment slides over a few hundred rows) and the ring of the last 15 rows
+      const int kk = k + u;
+      float* rp = ring + slot * (5 * MS_NT) + tx;
+#pragma unroll
+      for (int c = 0; c < 5; ++c) {
+        float inc = m[c];
+        if (kk >= 15) inc -= rp[c * MS_NT];
+        rp[c * MS_NT] = m[c];
+        const float yk = inc - comp[c], t = vs[c] + yk;
+        comp[c] = (t - vs[c]) - yk;
+        vs[c] = t;
+      }
+      slot = slot == 14 ? 0 : slot + 1;
+      if (kk >= 14) {
+        float* hp = hb + ((kk - 14) & (MS_RB - 1)) * (5 * MS_NT) + tx;
+#pragma unroll
+        for (int c = 0; c < 5; ++c) hp[c * MS_NT] = vs[c];
+      }
+    }
+    pbot = bot[1]; pq = q[1] + w;
+    if (k >= 16 && (k & 3) == 0) {
+      // rows ya + k - 16 .. ya + k - 13 are complete: horizontal 15-sums (slots o+1 .. o+15 for output o) + solve
+      __syncthreads();
+      if (tx < MS_RB * (MS_SX / 4)) {
+        const int j = tx / (MS_SX / 4), qd = tx - j * (MS_SX / 4);
+        const int gy = ya + k - 16 + j, gx0 = x0 + 4 * qd;
+        float g[5][4];
+#pragma unroll
+        for (int c = 0; c < 5; ++c) {
+          const float4* p = reinterpret_cast<const float4*>(hb + (j * 5 + c) * MS_NT + 4 * qd);
+          float wv[20];
+#pragma unroll
+          for (int i = 0; i < 5; ++i) { const float4 v = p[i]; wv[4 * i] = v.x; wv[4 * i + 1] = v.y; wv[4 * i + 2] = v.z; wv[4 * i + 3] = v.w; }
+          float s = 0.f;
+#pragma unroll
+          for (int i = 1; i <= 15; ++i) s += wv[i];
+          g[c][0] = s;
+#pragma unroll
+          for (int o = 1; o < 4; ++o) { s += wv[o + 15] - wv[o]; g[c][o] = s; }
+        }
+        if (gy < yb && gx0 < w) {
+          float2 f[4];
+#pragma unroll
+          for (int o = 0; o < 4; ++o) {
+            const double sc = 1.0 / 225.0;
+            const double g11 = g[0][o] * sc, g12 = g[1][o] * sc, g22 = g[2][o] * sc, h1 = g[3][o] * sc, h2 = g[4][o] * sc;
+            const double idet = 1.0 / (g11 * g22 - g12 * g12 + 1e-3);
+            f[o].x = (float)((g11 * h2 - g12 * h1) * idet);
+            f[o].y = (float)((g22 * h1 - g12 * h2) * idet);
+          }
+          const size_t oi = zo + (size_t)gy * w + gx0;
+          float2* dst = reinterpret_cast<float2*>(flow_out) + oi;
+          if (gx0 + 3 < w && (oi & 1) == 0 && (reinterpret_cast<uintptr_t>(flow_out) & 15) == 0) {
+            reinterpret_cast<float4*>(dst)[0] = make_float4(f[0].x, f[0].y, f[1].x, f[1].y);
+            reinterpret_cast<float4*>(dst)[1] = make_float4(f[2].x, f[2].y, f[3].x, f[3].y);
+          } else {
+#pragma unroll
+            for (int o = 0; o < 4; ++o) if (gx0 + o < w) dst[o] = f[o];
+          }
+        }
+      }
+      __syncthreads();
     }
   }
 }
@@ -623,6 +803,25 @@ static std::vector<Level> pyramid_plan(int H, int W) {
   return plan;
 }
 
+// rows per segment of the streaming iteration kernel: whole waves of the 2 x SM-count resident blocks, each block
+// paying 14 warm-up rows (+ ~6 rows' worth of fixed cost).  The running sums make the last bits depend on where a
+// segment starts, so the split is a function of (h, w) alone (sized for a nominal batch of 22 pairs = one 10 s clip):
+// results stay bit-identical for any batch size / GPU count.
+static int march_rows_per_seg(int h, int w, int sm_count) {
+  const int B = 22;
+  const long strips = cdiv(w, MS_SX), resident = 2L * sm_count;
+  double best = 1e30;
+  int best_rs = (h + 3) & ~3;
+  for (int nseg = 1; nseg <= cdiv(h, 8); ++nseg) {
+    const int rs = (cdiv(h, nseg) + 3) & ~3;
+    const long ctas = strips * cdiv(h, rs) * B;
+    const long waves = (ctas + resident - 1) / resident;
+    const double cost = (double)waves * (rs + 20);
+    if (cost < best) { best = cost; best_rs = rs; }
+  }
+  return best_rs;
+}
+
 }  // namespace b200vqa
 
 using namespace b200vqa;
@@ -650,6 +849,8 @@ extern "C" int b200vqa_farneback(b200vqa_t* h, const uint8_t* gray0, const uint8
   static bool attr_done = false;
   if (!attr_done) {
     VQA_CUDA(cudaFuncSetAttribute(k4_flow_iter, cudaFuncAttributeMaxDynamicSharedMemorySize, BX_SMEM));
+    VQA_CUDA(cudaFuncSetAttribute(k4_flow_iter_march<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MS_SMEM));
+    VQA_CUDA(cudaFuncSetAttribute(k4_flow_iter_march<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MS_SMEM));
     VQA_CUDA(cudaFuncSetAttribute(k4_pyr_level<0, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     VQA_CUDA(cudaFuncSetAttribute(k4_pyr_level<3, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     VQA_CUDA(cudaFuncSetAttribute(k4_pyr_level<9, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
@@ -696,6 +897,8 @@ extern "C" int b200vqa_farneback(b200vqa_t* h, const uint8_t* gray0, const uint8
       VQA_LAUNCH_CHECK();
     }
     const dim3 gbox(cdiv(L.w, BX_TX), cdiv(L.h, BX_TY), B);
+    const int rows_per_seg = march_rows_per_seg(L.h, L.w, h->sm_count);
+    const dim3 gmarch(cdiv(L.w, MS_SX), cdiv(L.h, rows_per_seg), B);
     float* fout = nullptr;
     for (int it = 0; it < 3; ++it) {
       fout = (last && it == 2) ? flow : (fin == flowA ? flowB : flowA);
@@ -705,7 +908,9 @@ extern "C" int b200vqa_farneback(b200vqa_t* h, const uint8_t* gray0, const uint8
         else { VQA_CUDA(cudaEventCreate(&ev.first)); VQA_CUDA(cudaEventCreate(&ev.second)); }
         VQA_CUDA(cudaEventRecord(ev.first, st));
       }
-      k4_flow_iter<<<gbox, 256, BX_SMEM, st>>>(RA0, RB0, RA1, RB1, fin, L.h, L.w, fout);
+      if (h->flow_impl == 0) k4_flow_iter_march<true><<<gmarch, MS_NT, MS_SMEM, st>>>(RA0, RB0, RA1, RB1, fin, L.h, L.w, rows_per_seg, fout);
+      else if (h->flow_impl == 1) k4_flow_iter_march<false><<<gmarch, MS_NT, MS_SMEM, st>>>(RA0, RB0, RA1, RB1, fin, L.h, L.w, rows_per_seg, fout);
+      else k4_flow_iter<<<gbox, 256, BX_SMEM, st>>>(RA0, RB0, RA1, RB1, fin, L.h, L.w, fout);
       if (h->profiling) {
         VQA_CUDA(cudaEventRecord(ev.second, st));
         h->prof_events_flow.push_back(ev);

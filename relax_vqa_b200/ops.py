@@ -57,6 +57,9 @@ class Context:
         check(self.lib.b200vqa_profile_read_flow(self.h, C.byref(ms), C.byref(n), C.byref(by)), "profile_read_flow")
         return ms.value, n.value, by.value
 
+    def set_flow_impl(self, impl):
+        check(self.lib.b200vqa_set_flow_impl(self.h, int(impl)), "set_flow_impl")
+
     def set_gemm_impl(self, impl):
         check(self.lib.b200vqa_set_gemm_impl(self.h, int(impl)), "set_gemm_impl")
 

@@ -7,6 +7,7 @@
 //   M                     structure-tensor entries: shared memory only (fused iteration kernel)
 //   flow[B][h][w][2]      f32  (dx, dy), ping-pong between levels
 #include <math.h>
+#include <stdlib.h>
 #include <vector>
 #include "context.h"
 
@@ -258,6 +259,163 @@ k4_polyexp(const float* __restrict__ I, const uint8_t* __restrict__ gray0, const
         RA[oo] = make_float4(b3 * pc.ig11, b2 * pc.ig11, b1 * pc.ig03 + b5 * pc.ig33, b1 * pc.ig03 + b4 * pc.ig33);
         RB[oo] = b6 * pc.ig55;
       }
+    }
+  }
+}
+
+// ---- (c), streaming form: one block owns a strip of PM_SX output columns (+ 5 halo columns each side) and marches
+// down a segment of rows, one thread per column with the 11 most recent rows of I in registers, so the vertical
+// 11-tap pass reads every input exactly once (the 64 x 16 tile kernel above re-reads 26/16 rows and re-filters
+// 74/64 columns).  Every PM_RB rows the three vertically filtered rows go through shared memory to the horizontal
+// pass (4 adjacent outputs per thread from aligned 128-bit windows).  Same arithmetic, in the same order, as
+// k4_polyexp: results are bit-identical.
+constexpr int PM_NT = 256, PM_SX = 244, PM_RB = 4;
+template <bool kFromGray>
+__global__ void __launch_bounds__(PM_NT, 3)
+k4_polyexp_march(const float* __restrict__ I, const uint8_t* __restrict__ gray0, const uint8_t* __restrict__ gray1, int B, int h, int w,
+                 int rows_per_seg, PolyConsts pc, float4* __restrict__ RA, float* __restrict__ RB) {
+  __shared__ __align__(16) float2 vb[PM_RB / 2][3][PM_NT];            // (row 2j, row 2j + 1) interleaved per column
+  const int tx = threadIdx.x, z = blockIdx.z;
+  const int x0 = blockIdx.x * PM_SX;
+  const int ya = blockIdx.y * rows_per_seg, yb = min(ya + rows_per_seg, h);
+  const int cx = min(max(x0 - PE_N + tx, 0), w - 1);                 // I is replicated outside the image
+  // input stage, fetched one iteration (two rows) ahead of its use.  Gray path: the 3x3 pre-blur (.25 .5 .25)^2 with
+  // REFLECT_101 is kept as exact integers: hrow(r) = g[r][x-1] + 2 g[r][x] + g[r][x+1]; moving down one row shifts
+  // (ha, hb, hc) = hrow(reflect(cy-1)), hrow(cy), hrow(reflect(cy+1)) and needs only the new third row.
+  const float* img = nullptr;
+  const uint8_t *gl = nullptr, *gc = nullptr, *gr = nullptr;
+  if (kFromGray) {
+    const uint8_t* g = (z < B ? gray0 + (size_t)z * h * w : gray1 + (size_t)(z - B) * h * w);
+    gl = g + reflect101(cx - 1, w); gc = g + cx; gr = g + reflect101(cx + 1, w);
+  } else {
+    img = I + (size_t)z * h * w + cx;
+  }
+  auto hrow = [&](int r) -> int { const int o = r * w; return (int)gl[o] + 2 * (int)gc[o] + (int)gr[o]; };
+  auto crow = [&](int k) -> int { return min(max(ya - PE_N + k, 0), h - 1); };        // image row of march step k
+  float win[11];
+#pragma unroll
+  for (int i = 0; i < 11; ++i) win[i] = 0.f;
+  int ha = 0, hb = 0, hc = 0, prev_cy = crow(0);
+  int hn[4] = {0, 0, 0, 0};                        // inputs of march steps k .. k + 3 (two iterations of look-ahead)
+  float fn[4] = {0.f, 0.f, 0.f, 0.f};
+  if (kFromGray) {
+    ha = hrow(reflect101(prev_cy - 1, h)); hb = hrow(prev_cy); hc = hrow(reflect101(prev_cy + 1, h));
+#pragma unroll
+    for (int u = 0; u < 4; ++u) hn[u] = hrow(reflect101(crow(u) + 1, h));
+  } else {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) fn[u] = img[(size_t)crow(u) * w];
+  }
+  const int nk = 10 + ((yb - ya + PM_RB - 1) & ~(PM_RB - 1));
+  for (int k = 0; k < nk; k += 2) {
+    float in2[2];
+    int hcur[2] = {hn[0], hn[1]};
+    if (kFromGray) {
+      hn[0] = hn[2]; hn[1] = hn[3];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) hn[2 + u] = hrow(reflect101(crow(k + 4 + u) + 1, h));
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int cy = crow(k + u);
+        if (cy != prev_cy) { ha = hb; hb = hc; hc = hcur[u]; prev_cy = cy; }
+        in2[u] = (float)(ha + 2 * hb + hc) * 0.0625f;     // integer sums / 16 are exactly OpenCV's two float passes
+      }
+    } else {
+#pragma unroll
+      for (int u = 0; u < 2; ++u) { in2[u] = fn[u]; fn[u] = fn[2 + u]; fn[2 + u] = img[(size_t)crow(k + 4 + u) * w]; }
+    }
+    float vr[2][3];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+#pragma unroll
+      for (int i = 0; i < 10; ++i) win[i] = win[i + 1];
+      win[10] = in2[u];
+      float r0 = win[5] * pc.g[0], r1 = 0.f, r2 = 0.f;
+#pragma unroll
+      for (int t = 1; t <= PE_N; ++t) {
+        const float up = win[5 - t], dn = win[5 + t], p = up + dn;
+        r0 = r0 + pc.g[t] * p;
+        r1 = r1 + pc.xg[t] * (dn - up);
+        r2 = r2 + pc.xxg[t] * p;
+      }
+      vr[u][0] = r0; vr[u][1] = r1; vr[u][2] = r2;
+    }
+    if (k >= 10) {                                  // k is even: output rows k - 10 and k - 9 form one interleaved pair
+      const int jp = ((k - 10) >> 1) & (PM_RB / 2 - 1);
+#pragma unroll
+      for (int a = 0; a < 3; ++a) vb[jp][a][tx] = make_float2(vr[0][a], vr[1][a]);
+    }
+    if (k >= 12 && (k & 3) == 0) {
+      // output rows ya + k - 12 .. ya + k - 9 are filtered vertically: horizontal pass, task = (row, 4 columns)
+      __syncthreads();
+      if (tx < (PM_RB / 2) * (PM_SX / 2)) {
+        // task = (row pair, column pair): both rows run through the packed fp32x2 pipe (FFMA2 / FADD2 on sm_100) with the
+        // tap as the broadcast operand; per lane this is the scalar sequence of k4_polyexp, so results are unchanged
+        const int jp = tx / (PM_SX / 2), cp = tx - jp * (PM_SX / 2);
+        const int gy = ya + k - 12 + 2 * jp;
+        const float2 neg1 = make_float2(-1.f, -1.f), zero2 = make_float2(0.f, 0.f);
+        float2 b1[2], b2[2], b3[2], b4[2], b5[2], b6[2];
+        {
+          float2 a[12];
+#pragma unroll
+          for (int i = 0; i < 6; ++i) { const float4 q = *reinterpret_cast<const float4*>(&vb[jp][0][cp * 2 + 2 * i]); a[2 * i] = make_float2(q.x, q.y); a[2 * i + 1] = make_float2(q.z, q.w); }
+#pragma unroll
+          for (int o = 0; o < 2; ++o) {
+            const int c = o + 5;
+            b1[o] = __fmul2_rn(a[c], make_float2(pc.g[0], pc.g[0])); b2[o] = zero2; b4[o] = zero2;
+#pragma unroll
+            for (int t = 1; t <= PE_N; ++t) {
+              const float2 tg = __fadd2_rn(a[c + t], a[c - t]);
+              b1[o] = __ffma2_rn(tg, make_float2(pc.g[t], pc.g[t]), b1[o]);
+              b4[o] = __ffma2_rn(tg, make_float2(pc.xxg[t], pc.xxg[t]), b4[o]);
+              b2[o] = __ffma2_rn(__ffma2_rn(a[c - t], neg1, a[c + t]), make_float2(pc.xg[t], pc.xg[t]), b2[o]);
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 6; ++i) { const float4 q = *reinterpret_cast<const float4*>(&vb[jp][1][cp * 2 + 2 * i]); a[2 * i] = make_float2(q.x, q.y); a[2 * i + 1] = make_float2(q.z, q.w); }
+#pragma unroll
+          for (int o = 0; o < 2; ++o) {
+            const int c = o + 5;
+            b3[o] = __fmul2_rn(a[c], make_float2(pc.g[0], pc.g[0])); b6[o] = zero2;
+#pragma unroll
+            for (int t = 1; t <= PE_N; ++t) {
+              b3[o] = __ffma2_rn(__fadd2_rn(a[c + t], a[c - t]), make_float2(pc.g[t], pc.g[t]), b3[o]);
+              b6[o] = __ffma2_rn(__ffma2_rn(a[c - t], neg1, a[c + t]), make_float2(pc.xg[t], pc.xg[t]), b6[o]);
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 6; ++i) { const float4 q = *reinterpret_cast<const float4*>(&vb[jp][2][cp * 2 + 2 * i]); a[2 * i] = make_float2(q.x, q.y); a[2 * i + 1] = make_float2(q.z, q.w); }
+#pragma unroll
+          for (int o = 0; o < 2; ++o) {
+            const int c = o + 5;
+            b5[o] = __fmul2_rn(a[c], make_float2(pc.g[0], pc.g[0]));
+#pragma unroll
+            for (int t = 1; t <= PE_N; ++t) b5[o] = __ffma2_rn(__fadd2_rn(a[c + t], a[c - t]), make_float2(pc.g[t], pc.g[t]), b5[o]);
+          }
+        }
+        const int gx0 = x0 + cp * 2;
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr) {
+          if (gy + rr < yb) {
+            const size_t row = (size_t)z * h * w + (size_t)(gy + rr) * w;
+            float xy[2];
+#pragma unroll
+            for (int o = 0; o < 2; ++o) {
+              const float v1 = rr ? b1[o].y : b1[o].x, v2 = rr ? b2[o].y : b2[o].x, v3 = rr ? b3[o].y : b3[o].x;
+              const float v4 = rr ? b4[o].y : b4[o].x, v5 = rr ? b5[o].y : b5[o].x, v6 = rr ? b6[o].y : b6[o].x;
+              xy[o] = v6 * pc.ig55;
+              if (gx0 + o < w) RA[row + gx0 + o] = make_float4(v3 * pc.ig11, v2 * pc.ig11, v1 * pc.ig03 + v5 * pc.ig33, v1 * pc.ig03 + v4 * pc.ig33);
+            }
+            if (gx0 + 1 < w && ((row + gx0) & 1) == 0 && (reinterpret_cast<uintptr_t>(RB) & 7) == 0) {
+              *reinterpret_cast<float2*>(RB + row + gx0) = make_float2(xy[0], xy[1]);
+            } else {
+#pragma unroll
+              for (int o = 0; o < 2; ++o) if (gx0 + o < w) RB[row + gx0 + o] = xy[o];
+            }
+          }
+        }
+      }
+      __syncthreads();
     }
   }
 }
@@ -581,22 +739,40 @@ k4_flow_iter_march(const float4* __restrict__ RA0, const float* __restrict__ RB0
   }
 }
 
-// ---- (f) flow upsample between levels: resize(prev, (w,h), INTER_LINEAR) * 2
+// ---- (f) flow upsample between levels: resize(prev, (w,h), INTER_LINEAR) * 2.  One thread per column walks UP_ROWS
+// rows: the column's source coordinates (double, as cv::resize computes them) are evaluated once, the rows' once per
+// block into shared memory.
+constexpr int UP_ROWS = 8;
 __global__ void __launch_bounds__(256)
 k4_flow_upsample(const float* __restrict__ prev, int hp, int wp, int h, int w, double sx, double sy, float* __restrict__ out) {
-  const int xo = blockIdx.x * blockDim.x + threadIdx.x, yo = blockIdx.y;
+  __shared__ int s_y0[UP_ROWS], s_y1[UP_ROWS];
+  __shared__ float s_ay[UP_ROWS];
+  const int xo = blockIdx.x * blockDim.x + threadIdx.x, yb = blockIdx.y * UP_ROWS;
+  if (threadIdx.x < UP_ROWS) {
+    const double s = (yb + threadIdx.x + 0.5) * sy - 0.5; int f = (int)floor(s); float ay = (float)(s - f);
+    int y0, y1;
+    if (f < 0) { f = 0; ay = 0.f; } y0 = f; y1 = f + 1; if (f >= hp - 1) { y0 = y1 = hp - 1; ay = 0.f; }
+    s_y0[threadIdx.x] = y0; s_y1[threadIdx.x] = y1; s_ay[threadIdx.x] = ay;
+  }
+  __syncthreads();
   if (xo >= w) return;
   const float2* p = reinterpret_cast<const float2*>(prev) + (size_t)blockIdx.z * hp * wp;
-  double s = (xo + 0.5) * sx - 0.5; int f = (int)floor(s); float ax = (float)(s - f);
-  int x0, x1, y0, y1;
+  const double s = (xo + 0.5) * sx - 0.5; int f = (int)floor(s); float ax = (float)(s - f);
+  int x0, x1;
   if (f < 0) { f = 0; ax = 0.f; } x0 = f; x1 = f + 1; if (f >= wp - 1) { x0 = x1 = wp - 1; ax = 0.f; }
-  s = (yo + 0.5) * sy - 0.5; f = (int)floor(s); float ay = (float)(s - f);
-  if (f < 0) { f = 0; ay = 0.f; } y0 = f; y1 = f + 1; if (f >= hp - 1) { y0 = y1 = hp - 1; ay = 0.f; }
-  const float2 p00 = p[(size_t)y0 * wp + x0], p01 = p[(size_t)y0 * wp + x1], p10 = p[(size_t)y1 * wp + x0], p11 = p[(size_t)y1 * wp + x1];
-  float2 o;
-  o.x = ((p00.x * (1.f - ax) + p01.x * ax) * (1.f - ay) + (p10.x * (1.f - ax) + p11.x * ax) * ay) * 2.f;
-  o.y = ((p00.y * (1.f - ax) + p01.y * ax) * (1.f - ay) + (p10.y * (1.f - ax) + p11.y * ax) * ay) * 2.f;
-  reinterpret_cast<float2*>(out)[((size_t)blockIdx.z * h + yo) * w + xo] = o;
+  float2* o = reinterpret_cast<float2*>(out) + ((size_t)blockIdx.z * h + yb) * w + xo;
+#pragma unroll
+  for (int r = 0; r < UP_ROWS; ++r) {
+    if (yb + r < h) {
+      const int y0 = s_y0[r], y1 = s_y1[r];
+      const float ay = s_ay[r];
+      const float2 p00 = p[(size_t)y0 * wp + x0], p01 = p[(size_t)y0 * wp + x1], p10 = p[(size_t)y1 * wp + x0], p11 = p[(size_t)y1 * wp + x1];
+      float2 v;
+      v.x = ((p00.x * (1.f - ax) + p01.x * ax) * (1.f - ay) + (p10.x * (1.f - ax) + p11.x * ax) * ay) * 2.f;
+      v.y = ((p00.y * (1.f - ax) + p01.y * ax) * (1.f - ay) + (p10.y * (1.f - ax) + p11.y * ax) * ay) * 2.f;
+      o[(size_t)r * w] = v;
+    }
+  }
 }
 
 // =========================================================================== flow colouring
@@ -803,6 +979,21 @@ static std::vector<Level> pyramid_plan(int H, int W) {
   return plan;
 }
 
+// rows per segment of the streaming expansion kernel (no running sums: the split does not change any result bit)
+static int poly_rows_per_seg(int h, int w, int images, int sm_count) {
+  const long strips = cdiv(w, PM_SX), resident = 3L * sm_count;
+  double best = 1e30;
+  int best_rs = (h + 3) & ~3;
+  for (int nseg = 1; nseg <= cdiv(h, 8); ++nseg) {
+    const int rs = (cdiv(h, nseg) + 3) & ~3;
+    const long ctas = strips * cdiv(h, rs) * images;
+    const long waves = (ctas + resident - 1) / resident;
+    const double cost = (double)waves * (rs + 14);
+    if (cost < best) { best = cost; best_rs = rs; }
+  }
+  return best_rs;
+}
+
 // rows per segment of the streaming iteration kernel: whole waves of the 2 x SM-count resident blocks, each block
 // paying 14 warm-up rows (+ ~6 rows' worth of fixed cost).  The running sums make the last bits depend on where a
 // segment starts, so the split is a function of (h, w) alone (sized for a nominal batch of 22 pairs = one 10 s clip):
@@ -857,6 +1048,7 @@ extern "C" int b200vqa_farneback(b200vqa_t* h, const uint8_t* gray0, const uint8
     VQA_CUDA(cudaFuncSetAttribute(k4_pyr_level<19, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     attr_done = true;
   }
+  static const bool poly_tile = getenv("B200VQA_POLY_TILE") != nullptr;      // A/B: 64 x 16 tile expansion kernel
   float* prev = nullptr;         // flow of the previous (coarser) level
   int ph = 0, pw = 0;
   for (size_t li = 0; li < plan.size(); ++li) {
@@ -866,9 +1058,12 @@ extern "C" int b200vqa_farneback(b200vqa_t* h, const uint8_t* gray0, const uint8
     const size_t lp = (size_t)L.h * L.w;
     const float4* RA0 = RA; const float4* RA1 = RA + (size_t)B * lp;
     const float* RB0 = RB; const float* RB1 = RB + (size_t)B * lp;
+    const int poly_rows = poly_rows_per_seg(L.h, L.w, 2 * B, h->sm_count);
+    const dim3 gpoly(cdiv(L.w, PM_SX), cdiv(L.h, poly_rows), 2 * B);
     if (L.h == H && L.w == W) {
       // finest level: 3x3 blur fused into the expansion (no f32 image in HBM)
-      k4_polyexp<true><<<dim3(cdiv(L.w, PE_TW), cdiv(L.h, PE_TH), 2 * B), 256, 0, st>>>(nullptr, gray0, gray1, B, L.h, L.w, pc, RA, RB);
+      if (h->flow_impl == 2 || poly_tile) k4_polyexp<true><<<dim3(cdiv(L.w, PE_TW), cdiv(L.h, PE_TH), 2 * B), 256, 0, st>>>(nullptr, gray0, gray1, B, L.h, L.w, pc, RA, RB);
+      else k4_polyexp_march<true><<<gpoly, PM_NT, 0, st>>>(nullptr, gray0, gray1, B, L.h, L.w, poly_rows, pc, RA, RB);
       VQA_LAUNCH_CHECK();
     } else {
       const double sx = (double)W / L.w, sy = (double)H / L.h;
@@ -884,7 +1079,8 @@ extern "C" int b200vqa_farneback(b200vqa_t* h, const uint8_t* gray0, const uint8
       else k4_pyr_level<0, 8><<<gpyr, 256, smem, st>>>(gray0, gray1, B, H, W, taps, L.h, L.w, sx, sy, I);
       VQA_LAUNCH_CHECK();
       // I holds [2B][h][w]; expansion of images 0..B-1 then B..2B-1 (contiguous)
-      k4_polyexp<false><<<dim3(cdiv(L.w, PE_TW), cdiv(L.h, PE_TH), 2 * B), 256, 0, st>>>(I, nullptr, nullptr, B, L.h, L.w, pc, RA, RB);
+      if (h->flow_impl == 2 || poly_tile) k4_polyexp<false><<<dim3(cdiv(L.w, PE_TW), cdiv(L.h, PE_TH), 2 * B), 256, 0, st>>>(I, nullptr, nullptr, B, L.h, L.w, pc, RA, RB);
+      else k4_polyexp_march<false><<<gpoly, PM_NT, 0, st>>>(I, nullptr, nullptr, B, L.h, L.w, poly_rows, pc, RA, RB);
       VQA_LAUNCH_CHECK();
     }
     float* fin = flowA;
@@ -893,7 +1089,7 @@ extern "C" int b200vqa_farneback(b200vqa_t* h, const uint8_t* gray0, const uint8
       count_launch();
     } else {
       fin = (prev == flowA) ? flowB : flowA;
-      k4_flow_upsample<<<dim3(cdiv(L.w, 256), L.h, B), 256, 0, st>>>(prev, ph, pw, L.h, L.w, (double)pw / L.w, (double)ph / L.h, fin);
+      k4_flow_upsample<<<dim3(cdiv(L.w, 256), cdiv(L.h, UP_ROWS), B), 256, 0, st>>>(prev, ph, pw, L.h, L.w, (double)pw / L.w, (double)ph / L.h, fin);
       VQA_LAUNCH_CHECK();
     }
     const dim3 gbox(cdiv(L.w, BX_TX), cdiv(L.h, BX_TY), B);

@@ -222,6 +222,38 @@ __device__ __forceinline__ void epi_row_fast(const float* __restrict__ bias, con
   }
 }
 
+// fp16-output row epilogue without shared memory (qkv / fc1 of the ViT: 7/12 of its FLOPs, K = 768).  At full tensor
+// rate the operand traffic of a K-block (TMA fill + MMA read) already saturates the 128 B/clk shared-memory port, so
+// the 2 x 128 KB the staged transposition moves per 128 x 256 tile is paid for in tensor throughput (12 K-blocks x
+// 64 KB of operands vs 256 KB of staging: -25 %).  Here each thread converts 32 consecutive columns of its own
+// accumulator row and writes them as one 64-byte segment (two full sectors) straight from registers.
+__device__ __forceinline__ void epi_row_direct_f16(const float* __restrict__ bias, __half* __restrict__ out, int M, int ldo, int act,
+                                                   int block_n, uint32_t taddr, int m, int n0, int grp) {
+  for (int c0 = grp * 32; c0 < block_n; c0 += 32 * GEMM_EPI_GROUPS) {
+    uint32_t v[32];
+    tmem_ld32(taddr + c0, v);
+    float4 b[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) b[i] = bias ? __ldg(reinterpret_cast<const float4*>(bias + n0 + c0) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    tmem_ld_wait();
+    if (m < M) {
+      uint32_t hv[16];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float x0 = __uint_as_float(v[4 * i]) + b[i].x, x1 = __uint_as_float(v[4 * i + 1]) + b[i].y;
+        float x2 = __uint_as_float(v[4 * i + 2]) + b[i].z, x3 = __uint_as_float(v[4 * i + 3]) + b[i].w;
+        if (act == ACT_GELU) { x0 = gelu_erf(x0); x1 = gelu_erf(x1); x2 = gelu_erf(x2); x3 = gelu_erf(x3); }
+        else if (act == ACT_RELU) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); x2 = fmaxf(x2, 0.f); x3 = fmaxf(x3, 0.f); }
+        const __half2 h0 = __floats2half2_rn(x0, x1), h1 = __floats2half2_rn(x2, x3);
+        hv[2 * i] = *reinterpret_cast<const uint32_t*>(&h0); hv[2 * i + 1] = *reinterpret_cast<const uint32_t*>(&h1);
+      }
+      uint4* op = reinterpret_cast<uint4*>(out + (size_t)m * ldo + n0 + c0);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) op[i] = make_uint4(hv[4 * i], hv[4 * i + 1], hv[4 * i + 2], hv[4 * i + 3]);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------ the kernel
 #ifdef B200VQA_GEMM_KERNEL_TU      // defined by gemm_host.cu only (one definition per library)
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
@@ -350,7 +382,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       } else if (p.epi == EPI_ROW) {
         const int m = mt * GEMM_BM + row;
         const int n0 = nt * p.block_n;
-        if ((p.block_n & 31) == 0 && n0 + p.block_n <= p.N) {
+        if ((p.block_n & 31) == 0 && n0 + p.block_n <= p.N && !p.out_is_f32 && !p.residual && (p.ldo & 7) == 0 && !(p.dbg_skip_epilogue & 8)) {
+          epi_row_direct_f16(p.bias, static_cast<__half*>(p.out), p.M, p.ldo, p.act, p.block_n, taddr, m, n0, grp);
+        } else if ((p.block_n & 31) == 0 && n0 + p.block_n <= p.N) {
           epi_row_fast(p.bias, p.residual, p.out, p.M, p.ldo, p.out_is_f32, p.act, p.block_n, taddr, epi_stage + (warp - 4) * (32 * EPI_LD),
                        mt * GEMM_BM + q * 32, n0, grp, lane);
         } else {
@@ -490,8 +524,20 @@ struct Gemm2Params {
   int act, M, N, ldo, out_is_f32;
   const float* bias; const float* residual; void* out;
   int dbg_skip_epilogue;
+  int raster;                    // 0: row-tile index fastest; G > 0: groups of G row tiles, walked row-tile fastest inside a group
 };
 constexpr int G2_BN = 256;
+// tile -> (row-tile pair m2, column tile nt).  With groups of G row tiles the 74 clusters of a wave share G A panels and
+// ~74/G B panels instead of streaming 74 different A panels against one B panel.
+__device__ __forceinline__ void g2_tile_coords(const Gemm2Params& p, int tile, int& m2, int& nt) {
+  if (p.raster <= 0) { m2 = tile % p.m2_tiles; nt = tile / p.m2_tiles; return; }
+  const int per_group = p.raster * p.n_tiles;
+  const int g = tile / per_group, r = tile - g * per_group;
+  const int m_first = g * p.raster;
+  const int gsize = min(p.raster, p.m2_tiles - m_first);
+  nt = r / gsize;
+  m2 = m_first + (r - nt * gsize);
+}
 constexpr uint32_t G2_STAGE_BYTES = 2 * GEMM_BM * GEMM_BK * 2;       // A 128x64 + B-half 128x64 (fp16) per CTA
 
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
@@ -560,7 +606,7 @@ gemm2cta_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-        const int m2 = tile % p.m2_tiles, nt = tile / p.m2_tiles;
+        int m2, nt; g2_tile_coords(p, tile, m2, nt);
         for (int kb = 0; kb < p.k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + (size_t)stage * G2_STAGE_BYTES;
@@ -614,13 +660,18 @@ gemm2cta_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
     const int q = warp & 3, grp = (warp - 4) >> 2;
     int acc = 0; uint32_t acc_phase = 0;
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-      const int m2 = tile % p.m2_tiles, nt = tile / p.m2_tiles;
+      int m2, nt; g2_tile_coords(p, tile, m2, nt);
       mbar_wait(&tmem_full[acc], acc_phase);
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t)acc * 256u + ((uint32_t)(q * 32) << 16);
-      if (!(p.dbg_skip_epilogue & 1))
+      if (p.dbg_skip_epilogue & 1) {
+      } else if (!p.out_is_f32 && !p.residual && (p.ldo & 7) == 0 && !(p.dbg_skip_epilogue & 8)) {
+        epi_row_direct_f16(p.bias, static_cast<__half*>(p.out), p.M, p.ldo, p.act, G2_BN, taddr,
+                           m2 * 256 + (int)rank * GEMM_BM + q * 32 + lane, nt * G2_BN, grp);
+      } else {
         epi_row_fast(p.bias, p.residual, p.out, p.M, p.ldo, p.out_is_f32, p.act, G2_BN, taddr, epi_stage + (warp - 4) * (32 * EPI_LD),
                      m2 * 256 + (int)rank * GEMM_BM + q * 32, nt * G2_BN, grp, lane);
+      }
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(&tmem_empty[acc], 0);

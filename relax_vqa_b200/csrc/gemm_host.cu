@@ -92,7 +92,7 @@ int launch_gemm_2cta(const CUtensorMap& map_a, const CUtensorMap& map_b, int M, 
   if (p.stages > GEMM_MAX_STAGES) p.stages = GEMM_MAX_STAGES;
   if (const char* e = getenv("B200VQA_GEMM_STAGES")) { int v = atoi(e); if (v >= 2 && v <= p.stages) p.stages = v; }
   if (const char* e = getenv("B200VQA_GEMM_NOEPI")) p.dbg_skip_epilogue = atoi(e);
-  p.raster = 0;
+  p.raster = 8;            // groups of 8 row-tile pairs: +4 % on the ViT linears over row-tile-fastest (profiles/r1_gemm_experiments.md)
   if (const char* e = getenv("B200VQA_GEMM_RASTER")) p.raster = atoi(e);
   p.act = act; p.M = M; p.N = N; p.ldo = N; p.out_is_f32 = out_is_f32; p.bias = bias; p.residual = residual; p.out = out;
   const size_t smem = (size_t)p.stages * G2_STAGE_BYTES + fixed;

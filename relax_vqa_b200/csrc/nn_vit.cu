@@ -403,9 +403,10 @@ extern "C" int b200vqa_vitb16_features(b200vqa_t* h, const uint8_t* img, int B, 
     VQA_CUDA(cudaFuncSetAttribute(k10_attention, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
     attr_done = true;
   }
-  // images per pass: 127 x 197 tokens = 98 row-tile pairs -> the 3 / 9 / 12 column tiles of the ViT linears fill the
-  // 74 SM pairs in whole waves (294, 882, 1176 tiles), avoiding a nearly empty trailing wave
-  const int CH = 127;
+  // images per pass: as many as the workspace allows (512 images = 1.3 GB).  Each of the 49 tcgen05 launches of a pass
+  // costs ~10 us of prologue / ramp / tail (tools/gemm_waves.py), and with >= 8 waves per launch the partial last wave
+  // matters less than that fixed cost (a 264-image step: 9 / 25 / 34 waves for the 3 / 9 / 12 column tiles).
+  const int CH = 512;
   const int passes = cdiv(B, CH);
   const int nb = cdiv(B, passes);                      // balanced passes
   const size_t M = (size_t)nb * VT;

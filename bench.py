@@ -224,10 +224,16 @@ def main():
                     launches_per_step=gemm_launches // 2, kernel_ms_per_step=gemm_ms / 2, share_of_step=(gemm_ms / 2) / step_ms,
                     algorithmic_gflop_per_pair=gemm_flops / 2 / (args.clips * PAIRS) / 1e9)
     flow_gbs = flow_bytes / (flow_ms / 1e3) / 1e9 if flow_ms > 0 else 0.0
-    roofline_hbm = dict(bound="hbm", kernel="k4_flow_iter", achieved=flow_gbs, peak=peaks["hbm_gbs"], unit="GB/s", frac=flow_gbs / peaks["hbm_gbs"],
-                        traffic=(flow_bytes / max(flow_launches, 1)) * (2.545 / 2.554), launches_per_step=flow_launches // 2, kernel_ms_per_step=flow_ms / 2,
-                        share_of_step=(flow_ms / 2) / step_ms, algorithmic_bytes_per_pixel_iteration=56,
-                        note="largest single bandwidth kernel; traffic = algorithmic bytes per launch x the ncu dram/algorithmic ratio measured on the level-0 launch (2.545 GB vs 2.554 GB, profiles/r1_ncu_full_flow_iter2.txt)")
+    ratio, fsrc = 1.0, None
+    fp = os.path.join(ROOT, "profiles", "r1_flow_traffic.json")
+    if os.path.exists(fp):          # dram bytes / algorithmic bytes of the level-0 launch from the committed ncu capture
+        fj = json.load(open(fp))
+        ratio, fsrc = fj["dram_over_algorithmic"], "profiles/r1_flow_traffic.json"
+    roofline_hbm = dict(bound="hbm", kernel="k4_flow_iter_march", achieved=flow_gbs, peak=peaks["hbm_gbs"], unit="GB/s", frac=flow_gbs / peaks["hbm_gbs"],
+                        traffic=(flow_bytes / max(flow_launches, 1)) * ratio if fsrc else None, launches_per_step=flow_launches // 2,
+                        kernel_ms_per_step=flow_ms / 2, share_of_step=(flow_ms / 2) / step_ms, algorithmic_bytes_per_pixel_iteration=56,
+                        note="largest single bandwidth kernel (Farneback iteration, 3 per pyramid level); traffic = algorithmic bytes per launch x "
+                             "the ncu dram/algorithmic ratio of the level-0 launch (%s)" % fsrc)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()

@@ -156,8 +156,9 @@ int b200vqa_set_gemm_impl(b200vqa_t* h, int impl);
  * b200vqa_profile_read synchronises, returns the summed device time (ms), the launch count and the
  * algorithmic FLOPs (2*M*N*K of the un-padded problems) since the last read, and resets them. */
 int b200vqa_set_profiling(b200vqa_t* h, int on);
-/* debug switch for the Farneback iteration (A/B measurements): 0 = streaming column-strip kernel with bilinear-tap
- * reuse (default), 1 = the same without tap reuse, 2 = the 48 x 32 tile kernel */
+/* debug switch for the Farneback kernels (A/B measurements): 0 = streaming column-strip iteration and expansion kernels
+ * (default; iteration with L2 look-ahead prefetch), 1 = the same without the prefetch, 2 = the earlier tile kernels
+ * (48 x 32 iteration tiles, 64 x 16 expansion tiles) */
 int b200vqa_set_flow_impl(b200vqa_t* h, int impl);
 int b200vqa_profile_read(b200vqa_t* h, double* gemm_ms, int64_t* gemm_launches, double* gemm_flops);
 /* same for the Farneback iteration kernel (k4_flow_iter): device ms, launches, algorithmic bytes (56 B per pixel) */

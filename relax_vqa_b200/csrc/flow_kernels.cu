@@ -586,7 +586,7 @@ __device__ __forceinline__ Tap2 ld_tap2(const float4* __restrict__ ra, const flo
   Tap2 t; t.a0 = ra[q]; t.a1 = ra[q + 1]; t.b0 = rb[q]; t.b1 = rb[q + 1]; return t;
 }
 
-template <bool kReuse>
+template <bool kReuse, bool kPrefetch>
 __global__ void __launch_bounds__(MS_NT, 2)
 k4_flow_iter_march(const float4* __restrict__ RA0, const float* __restrict__ RB0, const float4* __restrict__ RA1,
                    const float* __restrict__ RB1, const float* __restrict__ flow_in, int h, int w, int rows_per_seg,
@@ -609,9 +609,15 @@ k4_flow_iter_march(const float4* __restrict__ RA0, const float* __restrict__ RB0
 #pragma unroll
   for (int c = 0; c < 5; ++c) { vs[c] = 0.f; comp[c] = 0.f; }
   int slot = 0;
-  float2 dn[2];
+  // flow vectors head the dependent chain flow -> tap address -> taps: they are fetched two iterations ahead, and one
+  // iteration ahead their tap lines (and the R0 lines) are requested into L2, so the demand loads of an iteration find
+  // an L2 hit instead of a DRAM access (kPrefetch)
+  float2 dn[2], dnn[2];
 #pragma unroll
-  for (int u = 0; u < 2; ++u) dn[u] = fin[min(max(ya - 7 + u, 0), h - 1) * w + x];
+  for (int u = 0; u < 2; ++u) {
+    dn[u] = fin[min(max(ya - 7 + u, 0), h - 1) * w + x];
+    dnn[u] = fin[min(max(ya - 7 + 2 + u, 0), h - 1) * w + x];
+  }
   Tap2 pbot; pbot.a0 = pbot.a1 = make_float4(0.f, 0.f, 0.f, 0.f); pbot.b0 = pbot.b1 = 0.f;
   int pq = -1;                                                              // address of the row held in pbot
   for (int k = 0; k < nk; k += 2) {
@@ -640,7 +646,20 @@ k4_flow_iter_march(const float4* __restrict__ RA0, const float* __restrict__ RB0
       if (need[u]) topl[u] = ld_tap2(ra1, rb1, q[u]);
     }
 #pragma unroll
-    for (int u = 0; u < 2; ++u) dn[u] = fin[min(max(ya - 7 + k + 2 + u, 0), h - 1) * w + x];
+    for (int u = 0; u < 2; ++u) {
+      dn[u] = dnn[u];
+      const int yn = min(max(ya - 7 + k + 2 + u, 0), h - 1);
+      dnn[u] = fin[min(max(ya - 7 + k + 4 + u, 0), h - 1) * w + x];
+      if (kPrefetch) {
+        const int on = yn * w + x;
+        const int x1 = (int)floorf((float)x + dn[u].x), y1 = (int)floorf((float)yn + dn[u].y);
+        const int qn = min(max(y1, 0), h - 2) * w + min(max(x1, 0), w - 2) + w;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(ra0 + on));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(rb0 + on));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(ra1 + qn));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(rb1 + qn));
+      }
+    }
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
       const Tap2 prev = u == 0 ? pbot : bot[0];
@@ -865,11 +884,12 @@ __global__ void __launch_bounds__(1024)
 k5_flow_rgb_patchsum(const float* __restrict__ flow, int H, int W, const float* __restrict__ minmax, uint8_t* __restrict__ rgb,
                      uint32_t* __restrict__ sums) {
   __shared__ uint32_t part[4];
+  __shared__ double s_norm[2];
   const int gw = W >> 4, gh = H >> 4;
   if (threadIdx.y == 0 && threadIdx.x < 4) part[threadIdx.x] = 0;
+  if (threadIdx.y == 1 && threadIdx.x == 0) { double a, b; norm_consts(minmax + 2 * blockIdx.z, a, b); s_norm[0] = a; s_norm[1] = b; }   // one f64 division per block
   __syncthreads();
-  double sc, sh;
-  norm_consts(minmax + 2 * blockIdx.z, sc, sh);
+  const double sc = s_norm[0], sh = s_norm[1];
   const int x = blockIdx.x * 64 + threadIdx.x, y = blockIdx.y * 16 + threadIdx.y;
   uint32_t s = 0;
   if (x < W && y < H) {
@@ -1044,8 +1064,8 @@ extern "C" int b200vqa_farneback(b200vqa_t* h, const uint8_t* gray0, const uint8
   static bool attr_done = false;
   if (!attr_done) {
     VQA_CUDA(cudaFuncSetAttribute(k4_flow_iter, cudaFuncAttributeMaxDynamicSharedMemorySize, BX_SMEM));
-    VQA_CUDA(cudaFuncSetAttribute(k4_flow_iter_march<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MS_SMEM));
-    VQA_CUDA(cudaFuncSetAttribute(k4_flow_iter_march<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MS_SMEM));
+    VQA_CUDA(cudaFuncSetAttribute(k4_flow_iter_march<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MS_SMEM));
+    VQA_CUDA(cudaFuncSetAttribute(k4_flow_iter_march<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MS_SMEM));
     VQA_CUDA(cudaFuncSetAttribute(k4_pyr_level<0, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     VQA_CUDA(cudaFuncSetAttribute(k4_pyr_level<3, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     VQA_CUDA(cudaFuncSetAttribute(k4_pyr_level<9, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
@@ -1108,8 +1128,8 @@ extern "C" int b200vqa_farneback(b200vqa_t* h, const uint8_t* gray0, const uint8
         else { VQA_CUDA(cudaEventCreate(&ev.first)); VQA_CUDA(cudaEventCreate(&ev.second)); }
         VQA_CUDA(cudaEventRecord(ev.first, st));
       }
-      if (h->flow_impl == 0) k4_flow_iter_march<true><<<gmarch, MS_NT, MS_SMEM, st>>>(RA0, RB0, RA1, RB1, fin, L.h, L.w, rows_per_seg, fout);
-      else if (h->flow_impl == 1) k4_flow_iter_march<false><<<gmarch, MS_NT, MS_SMEM, st>>>(RA0, RB0, RA1, RB1, fin, L.h, L.w, rows_per_seg, fout);
+      if (h->flow_impl == 0) k4_flow_iter_march<true, true><<<gmarch, MS_NT, MS_SMEM, st>>>(RA0, RB0, RA1, RB1, fin, L.h, L.w, rows_per_seg, fout);
+      else if (h->flow_impl == 1) k4_flow_iter_march<true, false><<<gmarch, MS_NT, MS_SMEM, st>>>(RA0, RB0, RA1, RB1, fin, L.h, L.w, rows_per_seg, fout);
       else k4_flow_iter<<<gbox, 256, BX_SMEM, st>>>(RA0, RB0, RA1, RB1, fin, L.h, L.w, fout);
       if (h->profiling) {
         VQA_CUDA(cudaEventRecord(ev.second, st));

@@ -247,9 +247,12 @@ __device__ __forceinline__ void epi_row_direct_f16(const float* __restrict__ bia
         const __half2 h0 = __floats2half2_rn(x0, x1), h1 = __floats2half2_rn(x2, x3);
         hv[2 * i] = *reinterpret_cast<const uint32_t*>(&h0); hv[2 * i + 1] = *reinterpret_cast<const uint32_t*>(&h1);
       }
-      uint4* op = reinterpret_cast<uint4*>(out + (size_t)m * ldo + n0 + c0);
+      // two 256-bit stores (STG.256, sm_100): one full 32-byte sector per lane and instruction
+      __half* op = out + (size_t)m * ldo + n0 + c0;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) op[i] = make_uint4(hv[4 * i], hv[4 * i + 1], hv[4 * i + 2], hv[4 * i + 3]);
+      for (int i = 0; i < 2; ++i)
+        asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(op + 16 * i), "r"(hv[8 * i]), "r"(hv[8 * i + 1]), "r"(hv[8 * i + 2]),
+                     "r"(hv[8 * i + 3]), "r"(hv[8 * i + 4]), "r"(hv[8 * i + 5]), "r"(hv[8 * i + 6]), "r"(hv[8 * i + 7]) : "memory");
     }
   }
 }
@@ -382,7 +385,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       } else if (p.epi == EPI_ROW) {
         const int m = mt * GEMM_BM + row;
         const int n0 = nt * p.block_n;
-        if ((p.block_n & 31) == 0 && n0 + p.block_n <= p.N && !p.out_is_f32 && !p.residual && (p.ldo & 7) == 0 && !(p.dbg_skip_epilogue & 8)) {
+        if ((p.block_n & 31) == 0 && n0 + p.block_n <= p.N && !p.out_is_f32 && !p.residual && (p.ldo & 15) == 0 && !(p.dbg_skip_epilogue & 8)) {
           epi_row_direct_f16(p.bias, static_cast<__half*>(p.out), p.M, p.ldo, p.act, p.block_n, taddr, m, n0, grp);
         } else if ((p.block_n & 31) == 0 && n0 + p.block_n <= p.N) {
           epi_row_fast(p.bias, p.residual, p.out, p.M, p.ldo, p.out_is_f32, p.act, p.block_n, taddr, epi_stage + (warp - 4) * (32 * EPI_LD),
@@ -665,7 +668,7 @@ gemm2cta_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t)acc * 256u + ((uint32_t)(q * 32) << 16);
       if (p.dbg_skip_epilogue & 1) {
-      } else if (!p.out_is_f32 && !p.residual && (p.ldo & 7) == 0 && !(p.dbg_skip_epilogue & 8)) {
+      } else if (!p.out_is_f32 && !p.residual && (p.ldo & 15) == 0 && !(p.dbg_skip_epilogue & 8)) {
         epi_row_direct_f16(p.bias, static_cast<__half*>(p.out), p.M, p.ldo, p.act, G2_BN, taddr,
                            m2 * 256 + (int)rank * GEMM_BM + q * 32 + lane, nt * G2_BN, grp);
       } else {

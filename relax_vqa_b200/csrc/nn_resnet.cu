@@ -45,18 +45,27 @@ void free_resnet(ResNetWeights* r) {
 // ToTensor + Normalize applied here; zero padding is applied after normalisation, as in conv2d.
 __global__ void __launch_bounds__(256)
 k8_stem_im2col(const uint8_t* __restrict__ img, int is_bgr, __half* __restrict__ out, size_t npix) {
+  // per-block table of the 3 x 256 possible normalised values (same float expression as ToTensor + Normalize, rounded to
+  // fp16 once): the 42 IEEE divisions per thread become 3
+  __shared__ uint16_t lut[3][256];
+  {
+    const float mean[3] = {0.485f, 0.456f, 0.406f}, stdv[3] = {0.229f, 0.224f, 0.225f};
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const __half hv = __float2half_rn(((float)threadIdx.x / 255.0f - mean[c]) / stdv[c]);
+      lut[c][threadIdx.x] = *reinterpret_cast<const uint16_t*>(&hv);
+    }
+  }
+  __syncthreads();
   const size_t idx = (size_t)blockIdx.x * 256 + threadIdx.x;     // one thread = one kernel row of one output pixel
   const size_t pix = idx >> 3;
   if (pix >= npix) return;
   const int r = (int)(idx & 7);
   const int x = pix % 112, y = (pix / 112) % 112;
   const size_t n = pix / (112 * 112);
-  const float inv_std[3] = {1.0f / 0.229f, 1.0f / 0.224f, 1.0f / 0.225f};
-  const float mean[3] = {0.485f, 0.456f, 0.406f}, stdv[3] = {0.229f, 0.224f, 0.225f};
-  (void)inv_std;
-  float v[24];
+  uint32_t hv[24];
 #pragma unroll
-  for (int i = 0; i < 24; ++i) v[i] = 0.f;
+  for (int i = 0; i < 24; ++i) hv[i] = 0u;
   const int iy = y * 2 + r - 3;
   if (r < 7 && iy >= 0 && iy < 224) {
     const uint8_t* row = img + (n * 224 + iy) * (224 * 3);
@@ -65,16 +74,13 @@ k8_stem_im2col(const uint8_t* __restrict__ img, int is_bgr, __half* __restrict__
       const int ix = x * 2 + s - 3;
       if (ix >= 0 && ix < 224) {
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          const uint8_t px = row[ix * 3 + (is_bgr ? 2 - c : c)];
-          v[s * 3 + c] = ((float)px / 255.0f - mean[c]) / stdv[c];
-        }
+        for (int c = 0; c < 3; ++c) hv[s * 3 + c] = lut[c][row[ix * 3 + (is_bgr ? 2 - c : c)]];
       }
     }
   }
   uint32_t pk[12];
 #pragma unroll
-  for (int i = 0; i < 12; ++i) { __half2 h = __floats2half2_rn(v[2 * i], v[2 * i + 1]); pk[i] = *reinterpret_cast<uint32_t*>(&h); }
+  for (int i = 0; i < 12; ++i) pk[i] = hv[2 * i] | (hv[2 * i + 1] << 16);
   uint4* o = reinterpret_cast<uint4*>(out + pix * 192 + r * 24);
   o[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
   o[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);

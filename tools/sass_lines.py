@@ -26,9 +26,12 @@ for f in sorted(os.listdir(tmp)):
         if re.match(r"\s+/\*[0-9a-f]{4}\*/", l):
             seq.append(cur)
     break
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--print-source", "sass", "--csv"], capture_output=True, text=True).stdout
+# reports with several kernels: pass e.g. "--kernel-name regex:k5_flow --launch-count 1" after the three positional arguments
+out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--print-source", "sass", "--csv"] + sys.argv[4:], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 hdr, data = rows[1], rows[2:]
+if seq is not None and len(data) > len(seq):      # several launches of the kernel in the report: keep the first
+    data = data[:len(seq)]
 iI, iS = hdr.index("Instructions Executed"), hdr.index("# Samples")
 assert seq is not None and len(seq) == len(data), (None if seq is None else len(seq), len(data))
 by = defaultdict(lambda: [0.0, 0.0])

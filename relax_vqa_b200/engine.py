@@ -91,8 +91,18 @@ class Engine:
         dev = self.device
         return dict(full_resnet=stack[:nf], full_vit=vit[:nf], frag_stack=stack[nf:nf + npair],
                     frag_pool=pool[nf + npair:], frag_vit_ori=vit[nf:nf + npair], frag_vit_mer=vit[nf + npair:],
-                    full_off=torch.tensor(full_off, dtype=torch.int32, device=dev),
-                    pair_off=torch.tensor(pair_off, dtype=torch.int32, device=dev))
+                    full_off=self._offsets(tuple(full_off)), pair_off=self._offsets(tuple(pair_off)))
+
+    def _offsets(self, key):
+        """Row offsets per clip as a device int32 tensor.  Cached per distinct tuple: a pageable host-to-device copy
+        synchronises the host with the stream, which would stop it from queueing the next batch behind this one."""
+        cache = self.__dict__.setdefault("_offset_cache", {})
+        t = cache.get(key)
+        if t is None:
+            if len(cache) > 4096:
+                cache.clear()
+            t = cache[key] = torch.tensor(key, dtype=torch.int32, device=self.device)
+        return t
 
     def extract(self, clips: Sequence[Clip]):
         """-> features [V, 35203] fp32 on the device (layout of src/demo_test.py:171-175)."""
@@ -111,17 +121,18 @@ class Engine:
             score = (score / 100.0) * 4.0 + 1.0
         return feats, score
 
-    def predict_host(self, host_clips: Sequence[Sequence[torch.Tensor]], video_type=None):
-        """End-to-end entry with HOST (pinned) uint8 buffers: H2D copies, full path, D2H of the scores.
-        Copies are queued on a side stream, one event per clip, so the copy of clip i+1 overlaps the
-        fragment stages of clip i on the compute stream."""
+    def submit_host(self, host_clips: Sequence[Sequence[torch.Tensor]], video_type=None):
+        """Asynchronous end-to-end entry with HOST (pinned) uint8 buffers: queues the H2D copies on a side stream (one
+        event per clip, so the copy of clip i+1 overlaps the fragment stages of clip i), the full path on the current
+        stream and the D2H copy of the scores into a pinned buffer.  Returns a ticket for `result()`.  Submitting
+        batch k+1 before collecting batch k lets its copies run under batch k's kernels."""
         if not hasattr(self, "_copy_stream"):
             self._copy_stream = torch.cuda.Stream(self.device)
         main = torch.cuda.current_stream(self.device)
-        self._copy_stream.wait_stream(main)
         clips = []
         for f, n in host_clips:
             with torch.cuda.stream(self._copy_stream):
+                # blocks come from the copy stream's pool; record_stream defers their reuse until the kernels are done
                 df = f.to(self.device, non_blocking=True)
                 dn = n.to(self.device, non_blocking=True)
                 ev = torch.cuda.Event()
@@ -130,7 +141,22 @@ class Engine:
             dn.record_stream(main)
             clips.append(Clip(df, dn, ev))
         feats, score = self.predict(clips, video_type)
-        return feats, score.cpu()
+        host_score = torch.empty(score.shape, dtype=score.dtype, pin_memory=True)
+        host_score.copy_(score, non_blocking=True)
+        done = torch.cuda.Event()
+        done.record(main)
+        return feats, host_score, done
+
+    @staticmethod
+    def result(ticket):
+        """Waits for a `submit_host` ticket -> (features on the device, scores on the host)."""
+        feats, host_score, done = ticket
+        done.synchronize()
+        return feats, host_score
+
+    def predict_host(self, host_clips: Sequence[Sequence[torch.Tensor]], video_type=None):
+        """End-to-end entry with HOST (pinned) uint8 buffers: H2D copies, full path, D2H of the scores."""
+        return self.result(self.submit_host(host_clips, video_type))
 
 
 def synthetic_clips_on_device(n_clips, H, W, pairs, device, seed=0) -> List[Clip]:

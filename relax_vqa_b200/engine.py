@@ -49,15 +49,18 @@ class Engine:
         self.has_head = True
 
     def close(self):
+        for _, c in getattr(self, "_lane_list", [])[1:]:
+            c.close()
         self.ctx.close()
 
     # ---------------------------------------------------------------- per-clip image stages
-    def fragments(self, frames, nexts, keep_intermediates=False):
+    def fragments(self, frames, nexts, keep_intermediates=False, ctx=None):
         """A1-A8 for B pairs of one resolution: -> (ori_frag, merged_frag) [B,224,224,3] u8 BGR."""
+        ctx = ctx or self.ctx
         r = ops.absdiff_patchsum(frames, nexts, want_residual=False, want_gray=True)
         pos, cnt = ops.topk_patches(r["sums"])
         ori, diff = ops.gather_fragments(frames, nexts, pos, cnt)
-        flow = ops.farneback(self.ctx, r["gray0"], r["gray1"])
+        flow = ops.farneback(ctx, r["gray0"], r["gray1"])
         _, fsums, minmax = ops.flow_to_rgb(flow, want_rgb=False, want_sums=True)
         fpos, fcnt = ops.topk_patches(fsums)
         flow_frag, merged = ops.flow_fragment_merge(flow, minmax, fpos, fcnt, diff, want_flow_frag=keep_intermediates)
@@ -67,27 +70,77 @@ class Engine:
         return ori, merged
 
     # --------------------------------------------------------------------------- full path
+    #: clips whose image stages run side by side (each lane = one CUDA stream + one library context for its workspaces);
+    #: the coarse pyramid levels launch grids far smaller than the GPU, which neighbouring clips fill
+    LANES = 4
+
+    #: False = everything on the current stream, one clip after the other (clean per-kernel timings for profiling)
+    concurrent = True
+
+    @property
+    def launches(self):
+        """Kernels launched by this engine (all lanes)."""
+        return sum(c.launches for c in self._contexts())
+
+    def _contexts(self):
+        return [self.ctx] + [c for _, c in getattr(self, "_lane_list", [])[1:]]
+
+    def set_profiling(self, on):
+        for c in self._contexts():
+            c.set_profiling(on)
+
+    def profile_read_flow(self):
+        """-> (ms, launches, algorithmic bytes) of the Farneback iteration launches of all lanes since the last read."""
+        parts = [c.profile_read_flow() for c in self._contexts()]
+        return tuple(sum(p[i] for p in parts) for i in range(3))
+
+    def _lanes(self):
+        if not hasattr(self, "_lane_list"):
+            n = max(1, int(self.LANES))
+            self._lane_list = [(torch.cuda.Stream(self.device), self.ctx if i == 0 else ops.Context(self.device.index))
+                               for i in range(n)]
+            self._side = torch.cuda.Stream(self.device)
+        return self._lane_list
+
     def extract_blocks(self, clips: Sequence[Clip]):
         """-> dict of per-frame feature matrices stacked over clips + row offsets per clip."""
         ctx = self.ctx
+        main = torch.cuda.current_stream(self.device)
+        lanes = self._lanes() if self.concurrent else [(main, ctx)]
         full_rn, full_vt, oris, mers = [], [], [], []
         full_off, pair_off = [0], [0]
-        for c in clips:
-            if c.ready is not None:
-                torch.cuda.current_stream(self.device).wait_event(c.ready)
-            tp = c.nexts.shape[0]
-            ori, mer = self.fragments(c.frames[:tp], c.nexts)
-            oris.append(ori)
-            mers.append(mer)
-            full_rn.append(ops.resize_pil(ctx, c.frames, ops.BILINEAR))
-            full_vt.append(ops.resize_pil(ctx, c.frames, ops.LANCZOS))
+        for s, _ in lanes[:len(clips)]:
+            s.wait_stream(main)
+        for i, c in enumerate(clips):
+            s, lctx = lanes[i % len(lanes)]
+            with torch.cuda.stream(s):
+                if c.ready is not None:
+                    s.wait_event(c.ready)
+                tp = c.nexts.shape[0]
+                ori, mer = self.fragments(c.frames[:tp], c.nexts, ctx=lctx)
+                rn = ops.resize_pil(lctx, c.frames, ops.BILINEAR)
+                vt = ops.resize_pil(lctx, c.frames, ops.LANCZOS)
+            for t in (ori, mer, rn, vt, c.frames, c.nexts):
+                t.record_stream(s)
+                t.record_stream(main)
+            oris.append(ori); mers.append(mer); full_rn.append(rn); full_vt.append(vt)
             full_off.append(full_off[-1] + c.frames.shape[0])
             pair_off.append(pair_off[-1] + tp)
+        for s, _ in lanes[:len(clips)]:
+            main.wait_stream(s)
         nf, npair = full_off[-1], pair_off[-1]
         rn_in = torch.cat(full_rn + oris + mers)
         vt_in = torch.cat(full_vt + oris + mers)
+        # the two backbones on two streams: each launch is a persistent grid over all SMs, so the blocks of one network's
+        # next kernel start on the SMs the other network's last wave has already left
+        side = self._side if self.concurrent else main
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            vit = ops.vitb16_features(ctx, vt_in, is_bgr=True)
+        vt_in.record_stream(side)
+        vit.record_stream(main)
         stack, pool = ops.resnet50_features(ctx, rn_in, is_bgr=True, want_stack=True, want_pool=True)
-        vit = ops.vitb16_features(ctx, vt_in, is_bgr=True)
+        main.wait_stream(side)
         dev = self.device
         return dict(full_resnet=stack[:nf], full_vit=vit[:nf], frag_stack=stack[nf:nf + npair],
                     frag_pool=pool[nf + npair:], frag_vit_ori=vit[nf:nf + npair], frag_vit_mer=vit[nf + npair:],

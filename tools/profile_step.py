@@ -28,4 +28,4 @@ for _ in range(a.steps):
     eng.predict(clips, "live_vqc")
 torch.cuda.synchronize()
 torch.cuda.profiler.stop()
-print("done", eng.ctx.launches)
+print("done", eng.launches)

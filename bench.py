@@ -137,12 +137,13 @@ def main():
     import torch
     import torch.distributed as dist
     from relax_vqa_b200 import weights
-    from relax_vqa_b200.engine import Engine, synthetic_clips_on_device
+    from relax_vqa_b200.engine import Engine, bind_host_to_gpu, synthetic_clips_on_device
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    cpus = bind_host_to_gpu(local)                      # pinned staging buffers NUMA-local to this rank's GPU
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     warmup = max(args.warmup, 3)
@@ -267,7 +268,8 @@ def main():
                 config=dict(workload=WORKLOAD, width=W, height=H, pairs_per_clip=PAIRS, clips_per_gpu_per_step=args.clips,
                             timing="inputs larger than L2 (%.0f MB per step per GPU)" % (h2d / 1e6), parallelism=f"video-sharded x{world}"),
                 clocks=clocks, gpu_launches=int(launches),
-                e2e=dict(value=e2e_value, unit="videos/s", h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(4 * args.clips)),
+                e2e=dict(value=e2e_value, unit="videos/s", h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(4 * args.clips),
+                         host_cpus_bound=len(cpus) if cpus else None),
                 roofline=roofline, roofline_hbm=roofline_hbm, cpu_baseline=cpu)
     print(json.dumps(line))
     if world > 1:

@@ -3,7 +3,9 @@ import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from relax_vqa_b200 import weights
-from relax_vqa_b200.engine import Engine, synthetic_clips_on_device
+from relax_vqa_b200.engine import Engine, bind_host_to_gpu, synthetic_clips_on_device
+if os.environ.get("BIND"):
+    print("bound to", len(bind_host_to_gpu(0) or []), "cpus of", os.cpu_count(), flush=True)
 
 H, W, PAIRS, CLIPS, STEPS = 1080, 1920, 22, 4, 8
 eng = Engine(0, head_sd=weights.seeded_head_state_dict())

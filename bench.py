@@ -96,9 +96,13 @@ def cpu_reference_sample(n_pairs=1, threads=None):
     return (time.perf_counter() - t0) / n_pairs
 
 
+CPU_SAMPLE_PAIRS = 11       # half a clip: ~10 s of host work per sample on 16 cores
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU implementation of the path (Python reference -> the oracle port,
-    one backbone forward per image instead of the reference's 15, i.e. favourable to the CPU), all host threads."""
+    one backbone forward per image instead of the reference's 15, i.e. favourable to the CPU), all host threads.
+    A step = CPU_SAMPLE_PAIRS sampled 1080p pairs (a bounded sample of the 22-pair clip); K steps, capped at ~150 s."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -107,15 +111,19 @@ def run_reference(args):
     torch.set_num_threads(cores)
     for _ in range(min(args.warmup, 1)):
         cpu_reference_sample(1)
-    times = [cpu_reference_sample(1) for _ in range(max(1, min(args.steps, 3)))]
+    times, t_start = [], time.perf_counter()
+    for _ in range(max(1, args.steps)):
+        times.append(cpu_reference_sample(CPU_SAMPLE_PAIRS))
+        if time.perf_counter() - t_start > 150.0:
+            break
     per_pair = sum(times) / len(times)
     vps = 1.0 / (per_pair * PAIRS)
     line = dict(impl="reference", metric="videos_per_sec_1080p_e2e", value=vps, unit="videos/s", n_gpus=args.gpus, steps=len(times),
-                warmup=min(args.warmup, 1), ms_per_step=per_pair * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None,
+                warmup=min(args.warmup, 1), ms_per_step=per_pair * CPU_SAMPLE_PAIRS * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None,
                 dtype="f32", data="synthetic", config=dict(workload=WORKLOAD, width=W, height=H, pairs_per_clip=PAIRS),
                 cpu_baseline=dict(value=vps, unit="videos/s", cores=cores, kind="port",
-                                  sample="1 sampled 1080p pair (+1 full frame) per step through oracle/pipeline.py with cv2 Farneback; "
-                                         "per-clip time = 22 x per-pair time"),
+                                  sample=f"{CPU_SAMPLE_PAIRS} sampled 1080p pairs (+ their full frames) per step through oracle/pipeline.py with cv2 "
+                                         f"Farneback; per-clip time = 22 x per-pair time"),
                 e2e=dict(value=vps, unit="videos/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(line))
 
@@ -260,9 +268,10 @@ def main():
         return
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        per_pair = cpu_reference_sample(1)
+        per_pair = cpu_reference_sample(CPU_SAMPLE_PAIRS)
         cpu = dict(value=1.0 / (per_pair * PAIRS), unit="videos/s", cores=torch.get_num_threads(), kind="port",
-                   sample=f"1 sampled 1080p pair + 1 full frame through oracle/pipeline.py (cv2 Farneback), {per_pair:.1f} s; clip = 22 pairs")
+                   sample=f"{CPU_SAMPLE_PAIRS} sampled 1080p pairs + their full frames through oracle/pipeline.py (cv2 Farneback), "
+                          f"{per_pair * CPU_SAMPLE_PAIRS:.1f} s; clip = 22 pairs")
     line = dict(metric="videos_per_sec_1080p_e2e", value=value, unit="videos/s", n_gpus=world, steps=args.steps, warmup=warmup,
                 ms_per_step=step_ms, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f16", data="synthetic",
                 config=dict(workload=WORKLOAD, width=W, height=H, pairs_per_clip=PAIRS, clips_per_gpu_per_step=args.clips,

@@ -96,7 +96,7 @@ def cpu_reference_sample(n_pairs=1, threads=None):
     return (time.perf_counter() - t0) / n_pairs
 
 
-CPU_SAMPLE_PAIRS = 11       # half a clip: ~10 s of host work per sample on 16 cores
+CPU_SAMPLE_PAIRS = int(os.environ.get("B200VQA_CPU_SAMPLE_PAIRS", "11"))   # half a clip: ~10 s of host work per sample on 16 cores
 
 
 def run_reference(args):

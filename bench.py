@@ -34,7 +34,7 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+    """Samples SM clocks / throttle reasons during the timed region (NVML, the source of nvidia-smi's numbers)."""
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
@@ -46,6 +46,38 @@ class ClockSampler:
         self.marks.append(len(self.rows))
 
     def start(self):
+        """NVML from a polling thread of this process (what nvidia-smi itself reads, without a second process contending
+        for the driver while kernels are being launched); nvidia-smi -lms as the fallback."""
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            idx = self.index
+            vis = [v.strip() for v in os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",") if v.strip()]
+            if self.index < len(vis) and vis[self.index].isdigit():
+                idx = int(vis[self.index])
+            h = nv.nvmlDeviceGetHandleByIndex(idx)
+            get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+            mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+            masks = (0x8, 0x40, 0x20, 0x4)              # hw_slowdown, hw_thermal_slowdown, sw_thermal_slowdown, sw_power_cap
+            self.halt = threading.Event()
+
+            def poll():
+                while not self.halt.is_set():
+                    try:
+                        r = int(get_reasons(h))
+                        self.rows.append([str(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), str(mx)] +
+                                         ["Active" if r & m else "Not Active" for m in masks])
+                    except Exception:
+                        pass
+                    self.halt.wait(0.02)
+
+            self.t = threading.Thread(target=poll, daemon=True)
+            self.t.start()
+            self.proc = "nvml"
+            return
+        except Exception:
+            self.proc = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -63,7 +95,10 @@ class ClockSampler:
             return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
         time.sleep(0.12)                                 # let the sample that covers the end of the region arrive (100 ms polling:
                                                          # faster polling makes nvidia-smi contend with the kernel launches)
-        self.proc.terminate()
+        if self.proc == "nvml":
+            self.halt.set()
+        else:
+            self.proc.terminate()
         self.t.join(timeout=2)
         if len(self.marks) == 2:
             lo, hi = self.marks[0], max(self.marks[1] + 1, self.marks[0] + 1)
@@ -76,7 +111,8 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(n)
         mx = max((int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()), default=None)
-        return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=mx, reasons=sorted(reasons), samples=len(sm))
+        return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=mx, reasons=sorted(reasons), samples=len(sm),
+                    source="nvml" if self.proc == "nvml" else "nvidia-smi")
 
 
 def cpu_reference_sample(n_pairs=1, threads=None):

@@ -1117,7 +1117,7 @@ extern "C" int b200vqa_farneback(b200vqa_t* h, const uint8_t* gray0, const uint8
       VQA_LAUNCH_CHECK();
     }
     const dim3 gbox(cdiv(L.w, BX_TX), cdiv(L.h, BX_TY), B);
-    const int rows_per_seg = march_rows_per_seg(L.h, L.w, h->sm_count);
+    const int rows_per_seg = march_rows_per_seg(L.h, L.w, 148);      // fixed SM count: the split must not vary between devices
     const dim3 gmarch(cdiv(L.w, MS_SX), cdiv(L.h, rows_per_seg), B);
     float* fout = nullptr;
     for (int it = 0; it < 3; ++it) {

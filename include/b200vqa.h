@@ -157,7 +157,8 @@ int b200vqa_set_gemm_impl(b200vqa_t* h, int impl);
  * algorithmic FLOPs (2*M*N*K of the un-padded problems) since the last read, and resets them. */
 int b200vqa_set_profiling(b200vqa_t* h, int on);
 /* debug switch for the Farneback kernels (A/B measurements): 0 = streaming column-strip iteration and expansion kernels
- * (default; iteration with L2 look-ahead prefetch), 1 = the same without the prefetch, 2 = the earlier tile kernels
+ * (default; vertical box sums accumulated in f64 like OpenCV), 1 = the same with Kahan-compensated fp32 sums (6 % faster, but
+ * a 1e7:1 edge leaves rounding residue in the flat region below it), 2 = the earlier tile kernels
  * (48 x 32 iteration tiles, 64 x 16 expansion tiles) */
 int b200vqa_set_flow_impl(b200vqa_t* h, int impl);
 int b200vqa_profile_read(b200vqa_t* h, double* gemm_ms, int64_t* gemm_launches, double* gemm_flops);

@@ -33,7 +33,7 @@ struct b200vqa_ctx {
   int device = 0;
   int sm_count = 148;
   int gemm_impl = 0;                       // 0 tcgen05, 1 SIMT check kernels
-  int flow_impl = 0;                       // 0 streaming strip kernels, 1 same without L2 prefetch, 2 tile kernels
+  int flow_impl = 0;                       // 0 streaming strip kernels (f64 running sums), 1 same with Kahan fp32 sums, 2 tile kernels
   int64_t launches = 0;
   int profiling = 0;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;          // class 0: tcgen05 GEMM / conv launches

@@ -577,7 +577,7 @@ k4_flow_iter(const float4* __restrict__ RA0, const float* __restrict__ RB0, cons
 // every MS_RB rows the block turns the vertical sums into 15-column sums with aligned 128-bit shared-memory windows
 // (4 adjacent outputs per thread) and solves.  Halo recompute: 256/240 columns x (rows + 14)/rows instead of the
 // 1.92x of the 48 x 32 tile kernel; moving down a column the upper two bilinear taps of a row are the lower two of
-// the previous row whenever the displacement is locally smooth, so they are reused from registers (kReuse).
+// the previous row whenever the displacement is locally smooth, so they are reused from registers.
 constexpr int MS_SX = 240, MS_HALO = 8, MS_NT = 256, MS_RB = 4;
 constexpr int MS_SMEM = (15 * 5 * MS_NT + MS_RB * 5 * MS_NT) * 4;          // ring + row-batch buffer = 97,280 B
 struct Tap2 { float4 a0, a1; float b0, b1; };                              // columns x1, x1 + 1 of one R1 row
@@ -586,7 +586,7 @@ __device__ __forceinline__ Tap2 ld_tap2(const float4* __restrict__ ra, const flo
   Tap2 t; t.a0 = ra[q]; t.a1 = ra[q + 1]; t.b0 = rb[q]; t.b1 = rb[q + 1]; return t;
 }
 
-template <bool kReuse, bool kPrefetch>
+template <bool kDoubleSums, bool kPrefetch>
 __global__ void __launch_bounds__(MS_NT, 2)
 k4_flow_iter_march(const float4* __restrict__ RA0, const float* __restrict__ RB0, const float4* __restrict__ RA1,
                    const float* __restrict__ RB1, const float* __restrict__ flow_in, int h, int w, int rows_per_seg,
@@ -605,9 +605,14 @@ k4_flow_iter_march(const float4* __restrict__ RA0, const float* __restrict__ RB0
   const bool xedge = (unsigned)(x - 5) >= (unsigned)(w - 10);
   const float bwx = border_w(x, w);
   const int nk = 14 + ((yb - ya + MS_RB - 1) & ~(MS_RB - 1));               // rows of M this block walks (even)
+  // vertical running sums.  kDoubleSums: f64 accumulators, as OpenCV's own sliding sums (FarnebackUpdateFlow_Blur) - a strong
+  // edge that passed through the 15-row window leaves no residue in the sums of the flat region below it, whatever the
+  // dynamic range (tests/test_flow_streaming_model.py); same instruction count as the compensated fp32 sums (vs + comp),
+  // the conversions and adds run on the conversion / fp64 pipes beside the fp32 work.
+  double vd[5];
   float vs[5], comp[5];
 #pragma unroll
-  for (int c = 0; c < 5; ++c) { vs[c] = 0.f; comp[c] = 0.f; }
+  for (int c = 0; c < 5; ++c) { vd[c] = 0.0; vs[c] = 0.f; comp[c] = 0.f; }
   int slot = 0;
   // flow vectors head the dependent chain flow -> tap address -> taps: they are fetched two iterations ahead, and one
   // iteration ahead their tap lines (and the R0 lines) are requested into L2, so the demand loads of an iteration find
@@ -636,8 +641,8 @@ k4_flow_iter_march(const float4* __restrict__ RA0, const float* __restrict__ RB0
     }
     // lower tap rows are always fetched; upper rows only where they are not the previous row's lower taps
     Tap2 bot[2], topl[2]; bool need[2];
-    need[0] = !kReuse || q[0] != pq;
-    need[1] = !kReuse || q[1] != q[0] + w;
+    need[0] = q[0] != pq;
+    need[1] = q[1] != q[0] + w;
 #pragma unroll
     for (int u = 0; u < 2; ++u) bot[u] = ld_tap2(ra1, rb1, q[u] + w);
 #pragma unroll
@@ -699,12 +704,20 @@ k4_flow_iter_march(const float4* __restrict__ RA0, const float* __restrict__ RB0
       float* rp = ring + slot * (5 * MS_NT) + tx;
 #pragma unroll
       for (int c = 0; c < 5; ++c) {
-        float inc = m[c];
-        if (kk >= 15) inc -= rp[c * MS_NT];
-        rp[c * MS_NT] = m[c];
-        const float yk = inc - comp[c], t = vs[c] + yk;
-        comp[c] = (t - vs[c]) - yk;
-        vs[c] = t;
+        if (kDoubleSums) {
+          double inc = (double)m[c];
+          if (kk >= 15) inc -= (double)rp[c * MS_NT];      // exact in f64
+          rp[c * MS_NT] = m[c];
+          vd[c] += inc;
+          vs[c] = (float)vd[c];
+        } else {
+          float inc = m[c];
+          if (kk >= 15) inc -= rp[c * MS_NT];
+          rp[c * MS_NT] = m[c];
+          const float yk = inc - comp[c], t = vs[c] + yk;
+          comp[c] = (t - vs[c]) - yk;
+          vs[c] = t;
+        }
       }
       slot = slot == 14 ? 0 : slot + 1;
       if (kk >= 14) {
@@ -1065,7 +1078,7 @@ extern "C" int b200vqa_farneback(b200vqa_t* h, const uint8_t* gray0, const uint8
   if (!attr_done) {
     VQA_CUDA(cudaFuncSetAttribute(k4_flow_iter, cudaFuncAttributeMaxDynamicSharedMemorySize, BX_SMEM));
     VQA_CUDA(cudaFuncSetAttribute(k4_flow_iter_march<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MS_SMEM));
-    VQA_CUDA(cudaFuncSetAttribute(k4_flow_iter_march<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MS_SMEM));
+    VQA_CUDA(cudaFuncSetAttribute(k4_flow_iter_march<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MS_SMEM));
     VQA_CUDA(cudaFuncSetAttribute(k4_pyr_level<0, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     VQA_CUDA(cudaFuncSetAttribute(k4_pyr_level<3, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     VQA_CUDA(cudaFuncSetAttribute(k4_pyr_level<9, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
@@ -1129,7 +1142,7 @@ extern "C" int b200vqa_farneback(b200vqa_t* h, const uint8_t* gray0, const uint8
         VQA_CUDA(cudaEventRecord(ev.first, st));
       }
       if (h->flow_impl == 0) k4_flow_iter_march<true, true><<<gmarch, MS_NT, MS_SMEM, st>>>(RA0, RB0, RA1, RB1, fin, L.h, L.w, rows_per_seg, fout);
-      else if (h->flow_impl == 1) k4_flow_iter_march<true, false><<<gmarch, MS_NT, MS_SMEM, st>>>(RA0, RB0, RA1, RB1, fin, L.h, L.w, rows_per_seg, fout);
+      else if (h->flow_impl == 1) k4_flow_iter_march<false, true><<<gmarch, MS_NT, MS_SMEM, st>>>(RA0, RB0, RA1, RB1, fin, L.h, L.w, rows_per_seg, fout);
       else k4_flow_iter<<<gbox, 256, BX_SMEM, st>>>(RA0, RB0, RA1, RB1, fin, L.h, L.w, fout);
       if (h->profiling) {
         VQA_CUDA(cudaEventRecord(ev.second, st));

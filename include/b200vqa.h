@@ -36,6 +36,11 @@ extern "C" {
 #define B200VQA_RESNET_POOL 2051
 #define B200VQA_VIT_POOL 2304
 #define B200VQA_FEATURES 35203
+/* floats per image of b200vqa_resnet50_maps: the 15 hooked activations (64x112x112, 3 x 256x56x56, 4 x 512x28x28,
+ * 4 x 1024x14x14, 3 x 2048x7x7), main_fragment_layerstack.py:91-95 */
+#define B200VQA_RESNET_MAP_FLOATS 5920768
+#define B200VQA_VIT_TOKENS 196
+#define B200VQA_VIT_DIM 768
 
 #define B200VQA_FILTER_BILINEAR 0 /* PIL BILINEAR (antialiased), visualise_resnet.py:41 */
 #define B200VQA_FILTER_LANCZOS 1  /* PIL LANCZOS, visualise_vit_layer.py:469 */
@@ -130,6 +135,15 @@ int b200vqa_resnet50_features(b200vqa_t* h, const uint8_t* img, int B, int is_bg
 int b200vqa_vitb16_features(b200vqa_t* h, const uint8_t* img, int B, int is_bgr, float* out,
                             void* stream);
 
+/* ---- boundary fidelity (debug / drop-in path, not the fused fast path): the RAW arrays the reference's per-image
+ * extractors return before the host pools them.
+ * b200vqa_resnet50_maps: the 15 hooked activations of visualise_resnet.process_video_frame (visualise_resnet.py:62-109)
+ * as fp32 (C,H,W) arrays, concatenated in hook order: maps [B][B200VQA_RESNET_MAP_FLOATS].  conv1 is the raw convolution
+ * output (hooked before bn1/relu); the avgpool hook of visualise_resnet_layer.py:62-102 is the spatial mean of the last map.
+ * b200vqa_vitb16_tokens: norm(x)[:, 1:] of visualise_vit_layer.py:234-239 / :492-500: tokens [B][196][768] fp32. */
+int b200vqa_resnet50_maps(b200vqa_t* h, const uint8_t* img, int B, int is_bgr, float* maps, void* stream);
+int b200vqa_vitb16_tokens(b200vqa_t* h, const uint8_t* img, int B, int is_bgr, float* tokens, void* stream);
+
 /* ---- A16: per-video temporal mean of each block and concatenation into [V][35203]
  * (demo_test.py:171-175).  full_* have rows [full_off[v], full_off[v+1]); frag_* rows
  * [pair_off[v], pair_off[v+1]).  Offsets are device int32 arrays of length V+1. */
@@ -152,6 +166,10 @@ int64_t b200vqa_launch_count(b200vqa_t* h);
 /* debug switch: 0 = tcgen05 (default; linear layers on the 2-CTA cta_group::2 kernel), 1 = SIMT check kernels for
  * every GEMM/conv, 2 = tcgen05 with the 1-CTA kernel everywhere (A/B measurements) */
 int b200vqa_set_gemm_impl(b200vqa_t* h, int impl);
+/* scheduling knob: persistent tcgen05 GEMM / conv grids of this context occupy at most `sms` SMs (even; 0 = all), leaving
+ * the rest of the GPU to kernels running concurrently on other streams (the bandwidth stages of the next batch).  Results
+ * do not depend on it (tiles are computed identically whichever CTA takes them). */
+int b200vqa_set_gemm_sms(b200vqa_t* h, int sms);
 /* profiling: when on, every tcgen05 GEMM/conv launch is bracketed by CUDA events on its stream.
  * b200vqa_profile_read synchronises, returns the summed device time (ms), the launch count and the
  * algorithmic FLOPs (2*M*N*K of the un-padded problems) since the last read, and resets them. */

@@ -332,19 +332,32 @@ def hsv2bgr_u8(hsv):
     return np.clip(out, 0, 255).astype(np.uint8)
 
 
+def _cv_normalize_minmax_255(m):
+    """cv2.normalize(m, None, 0, 255, NORM_MINMAX) on float32 (third-party, opencv-python 4.9.0.80 pinned by the reference's
+    requirements.txt:73; behaviour probed on cv2 4.13): scale = (float)(255 * (1 / (max - min))) with the division in double,
+    shift = -(min * scale) with the float32 scale, then dst = fma(src, scale, shift) in float32 (convertTo's 32f -> 32f
+    path).  Bit-identical to cv2 on every probe (tests/test_oracle_flow.py::test_normalize_twice_is_cv2_exact)."""
+    mn, mx = float(m.min()), float(m.max())
+    sc = F32(255.0 * (1.0 / (mx - mn)) if mx - mn > 2.220446049250313e-16 else 0.0)
+    a, b = np.float64(sc), np.float64(F32(-(F32(mn) * sc)))
+    return (m.astype(np.float64) * a + b).astype(F32)       # the double product of two floats is exact -> one rounding = fma
+
+
+def cv_magnitude(dx, dy):
+    """cv2.cartToPolar's magnitude: sqrt(fma(x, x, fl(y*y))) in float32 (bit-identical to cv2 4.13 on every probe)."""
+    yy = (dy.astype(F32) * dy.astype(F32)).astype(F32)
+    return np.sqrt((dx.astype(np.float64) * dx.astype(np.float64) + yy.astype(np.float64)).astype(F32)).astype(F32)
+
+
 def flow_to_rgb(flow):
-    """flow_to_rgb - src/main_fragment_layerstack.py:162-175 (returns BGR like the reference)."""
+    """flow_to_rgb - src/main_fragment_layerstack.py:162-175 (returns BGR like the reference).  The reference
+    normalises the magnitude TWICE (mag, then again for hsv[..., 2]); both passes are restated in cv2's float32
+    arithmetic."""
     dx = flow[..., 0].astype(F32)
     dy = flow[..., 1].astype(F32)
-    mag = np.sqrt(dx * dx + dy * dy).astype(F32)
+    mag = cv_magnitude(dx, dy)
     ang = (fast_atan2_deg(dy, dx) * F32(np.pi / 180.0)).astype(F32)
-    mn, mx = float(mag.min()), float(mag.max())
-    if mx - mn > 2.220446049250313e-16:
-        sc = 255.0 / (mx - mn)
-    else:
-        sc = 0.0
-    shift = 0.0 - mn * sc
-    magn = (mag.astype(np.float64) * sc + shift).astype(F32)
+    magn = _cv_normalize_minmax_255(_cv_normalize_minmax_255(mag))
     hue = ang * 180 / np.pi / 2            # float32 array arithmetic, as in the reference
     hsv = np.zeros(flow.shape[:2] + (3,), dtype=np.uint8)
     hsv[..., 0] = hue.astype(np.uint8) if hue.dtype != np.uint8 else hue

@@ -36,11 +36,14 @@ SIGNATURES = {
     "b200vqa_load_head": (c_int, [c_void_p, c_int] + [c_void_p] * 13),
     "b200vqa_resnet50_features": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "b200vqa_vitb16_features": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "b200vqa_resnet50_maps": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "b200vqa_vitb16_tokens": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "b200vqa_temporal_mean_concat": (c_int, [c_void_p] * 8 + [c_int, c_void_p, c_void_p]),
     "b200vqa_head_forward": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "b200vqa_gemm_f16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "b200vqa_launch_count": (c_int64, [c_void_p]),
     "b200vqa_set_gemm_impl": (c_int, [c_void_p, c_int]),
+    "b200vqa_set_gemm_sms": (c_int, [c_void_p, c_int]),
     "b200vqa_set_profiling": (c_int, [c_void_p, c_int]),
     "b200vqa_set_flow_impl": (c_int, [c_void_p, c_int]),
     "b200vqa_profile_read": (c_int, [c_void_p, C.POINTER(C.c_double), C.POINTER(c_int64), C.POINTER(C.c_double)]),

@@ -55,6 +55,8 @@ extern "C" int b200vqa_create(int device, b200vqa_t** out) {
     snprintf(g_last_error, sizeof g_last_error, "device %d is sm_%d%d; libb200vqa is built for sm_100a only", device, prop.major, prop.minor);
     return B200VQA_ECUDA;
   }
+  int rc;
+  if ((rc = flow_init_device_attrs()) || (rc = gemm_init_device_attrs()) || (rc = vit_init_device_attrs())) return rc;
   b200vqa_ctx* h = new b200vqa_ctx();
   h->device = device;
   h->sm_count = prop.multiProcessorCount;
@@ -81,6 +83,12 @@ extern "C" int64_t b200vqa_launch_count(b200vqa_t* h) { return h ? h->launches :
 extern "C" int b200vqa_set_gemm_impl(b200vqa_t* h, int impl) {
   if (!h || impl < 0 || impl > 2) return B200VQA_EINVAL;
   h->gemm_impl = impl;
+  return B200VQA_OK;
+}
+
+extern "C" int b200vqa_set_gemm_sms(b200vqa_t* h, int sms) {
+  if (!h || sms < 0 || (sms & 1)) return B200VQA_EINVAL;
+  h->gemm_sms = sms;
   return B200VQA_OK;
 }
 

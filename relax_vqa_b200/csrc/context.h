@@ -32,6 +32,7 @@ struct HeadWeights;           // nn_head.cu
 struct b200vqa_ctx {
   int device = 0;
   int sm_count = 148;
+  int gemm_sms = 0;                        // > 0: persistent tcgen05 grids use this many SMs (b200vqa_set_gemm_sms)
   int gemm_impl = 0;                       // 0 tcgen05, 1 SIMT check kernels
   int flow_impl = 0;                       // 0 streaming strip kernels (f64 running sums), 1 same with Kahan fp32 sums, 2 tile kernels
   int64_t launches = 0;
@@ -51,9 +52,18 @@ struct b200vqa_ctx {
 namespace b200vqa {
 extern thread_local b200vqa_ctx* g_ctx;
 struct CtxScope {             // routes launch counting to the context for the current call
-  explicit CtxScope(b200vqa_ctx* h) { g_launch_counter = h ? &h->launches : nullptr; g_ctx = h; }
+  explicit CtxScope(b200vqa_ctx* h) {
+    g_launch_counter = h ? &h->launches : nullptr; g_ctx = h;
+    if (h) cudaSetDevice(h->device);     // every handle-taking entry point runs on the context's device, whatever the caller's current one
+  }
   ~CtxScope() { g_launch_counter = nullptr; g_ctx = nullptr; }
 };
+// SMs a persistent tcgen05 grid of this context may occupy (even, >= 2)
+inline int gemm_grid_sms(const b200vqa_ctx* h) { return (h->gemm_sms > 0 && h->gemm_sms < h->sm_count) ? h->gemm_sms : h->sm_count; }
+// cudaFuncSetAttribute is per device: each translation unit sets its kernels' attributes for the CURRENT device
+int flow_init_device_attrs();
+int gemm_init_device_attrs();
+int vit_init_device_attrs();
 void free_resnet(ResNetWeights*);
 void free_vit(ViTWeights*);
 void free_head(HeadWeights*);

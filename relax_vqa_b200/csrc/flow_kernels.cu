@@ -812,8 +812,9 @@ k4_flow_upsample(const float* __restrict__ prev, int hp, int wp, int h, int w, d
 }
 
 // =========================================================================== flow colouring
+// cv2.cartToPolar's magnitude: sqrt(fma(x, x, fl(y*y))) (bit-identical to cv2 4.13: oracle/farneback.py::cv_magnitude)
 __device__ __forceinline__ float magnitude(float dx, float dy) {
-  return __fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
+  return __fsqrt_rn(__fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
 }
 
 __global__ void k5_minmax_init(float* minmax, int B) {
@@ -861,10 +862,13 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x) {
 }
 
 // flow vector -> BGR uint8 triple, exactly flow_to_rgb (src/main_fragment_layerstack.py:162-175)
-__device__ __forceinline__ uchar3 flow_colour(float dx, float dy, double nscale, double nshift) {
+// The reference normalises the magnitude twice (mag = normalize(mag); hsv[..., 2] = normalize(mag)); cv2.normalize on
+// float32 is dst = fma(src, scale, shift) with scale = (float)(255 * (1 / (max - min))) (double division), shift = -(min * scale).
+struct NormConsts { float a1, b1, a2, b2; };
+__device__ __forceinline__ uchar3 flow_colour(float dx, float dy, const NormConsts nc) {
   const float mag = magnitude(dx, dy);
   const float ang = __fmul_rn(fast_atan2_deg(dy, dx), 0.01745329238474369f);             // radians (float32(pi/180))
-  const float magn = (float)__dadd_rn(__dmul_rn((double)mag, nscale), nshift);    // cv2.normalize (double scale/shift)
+  const float magn = __fmaf_rn(__fmaf_rn(mag, nc.a1, nc.b1), nc.a2, nc.b2);
   const float hue = __fmul_rn(__fdiv_rn(__fmul_rn(ang, 180.f), 3.1415927410125732f), 0.5f);
   const int H8 = (int)hue & 255, V8 = (int)fminf(fmaxf(magn, 0.f), 255.f);
   // cv2 HSV2BGR (8-bit, hrange 180): S = 255 -> s = 1
@@ -886,10 +890,18 @@ __device__ __forceinline__ uchar3 flow_colour(float dx, float dy, double nscale,
                      (unsigned char)fminf(fmaxf(r, 0.f), 255.f));
 }
 
-__device__ __forceinline__ void norm_consts(const float* minmax, double& sc, double& sh) {
-  const double mn = minmax[0], mx = minmax[1];
-  sc = (mx - mn > 2.220446049250313e-16) ? 255.0 / (mx - mn) : 0.0;
-  sh = 0.0 - mn * sc;
+__device__ __forceinline__ void norm_pass(float mn, float mx, float& a, float& b) {
+  const double dmn = mn, dmx = mx;
+  const double sc = (dmx - dmn > 2.220446049250313e-16) ? 255.0 * (1.0 / (dmx - dmn)) : 0.0;
+  a = (float)sc;
+  b = -__fmul_rn(mn, a);                 // cv2 4.13: the shift uses the float32-rounded scale (probed: oracle/farneback.py)
+}
+__device__ __forceinline__ NormConsts norm_consts(const float* minmax) {
+  NormConsts nc;
+  norm_pass(minmax[0], minmax[1], nc.a1, nc.b1);
+  // the first pass is monotone, so the extrema of its output are the images of the extrema
+  norm_pass(__fmaf_rn(minmax[0], nc.a1, nc.b1), __fmaf_rn(minmax[1], nc.a1, nc.b1), nc.a2, nc.b2);
+  return nc;
 }
 
 // colour + 16x16 patch sums (+ optional image store).  block = 64 px x 16 rows (4 patches).
@@ -897,18 +909,18 @@ __global__ void __launch_bounds__(1024)
 k5_flow_rgb_patchsum(const float* __restrict__ flow, int H, int W, const float* __restrict__ minmax, uint8_t* __restrict__ rgb,
                      uint32_t* __restrict__ sums) {
   __shared__ uint32_t part[4];
-  __shared__ double s_norm[2];
+  __shared__ NormConsts s_norm;
   const int gw = W >> 4, gh = H >> 4;
   if (threadIdx.y == 0 && threadIdx.x < 4) part[threadIdx.x] = 0;
-  if (threadIdx.y == 1 && threadIdx.x == 0) { double a, b; norm_consts(minmax + 2 * blockIdx.z, a, b); s_norm[0] = a; s_norm[1] = b; }   // one f64 division per block
+  if (threadIdx.y == 1 && threadIdx.x == 0) s_norm = norm_consts(minmax + 2 * blockIdx.z);      // two f64 divisions per block
   __syncthreads();
-  const double sc = s_norm[0], sh = s_norm[1];
+  const NormConsts nc = s_norm;
   const int x = blockIdx.x * 64 + threadIdx.x, y = blockIdx.y * 16 + threadIdx.y;
   uint32_t s = 0;
   if (x < W && y < H) {
     const size_t p = ((size_t)blockIdx.z * H + y) * W + x;
     const float2 d = reinterpret_cast<const float2*>(flow)[p];
-    const uchar3 c = flow_colour(d.x, d.y, sc, sh);
+    const uchar3 c = flow_colour(d.x, d.y, nc);
     if (rgb) { rgb[p * 3] = c.x; rgb[p * 3 + 1] = c.y; rgb[p * 3 + 2] = c.z; }
     s = (uint32_t)c.x + c.y + c.z;
   }
@@ -932,10 +944,9 @@ k5_flow_fragment_merge(const float* __restrict__ flow, const float* __restrict__
   uchar3 col = make_uchar3(0, 0, 0);
   if (j < count[b]) {
     const int py = pos[((size_t)b * top_n + j) * 2], px = pos[((size_t)b * top_n + j) * 2 + 1];
-    double sc, sh;
-    norm_consts(minmax + 2 * b, sc, sh);
+    const NormConsts nc = norm_consts(minmax + 2 * b);
     const float2 d = reinterpret_cast<const float2*>(flow)[((size_t)b * H + py * 16 + r) * W + px * 16 + c];
-    col = flow_colour(d.x, d.y, sc, sh);
+    col = flow_colour(d.x, d.y, nc);
   }
   const size_t o = (((size_t)b * 224 + cy * 16 + r) * 224 + cx * 16 + c) * 3;
   if (flow_frag) { flow_frag[o] = col.x; flow_frag[o + 1] = col.y; flow_frag[o + 2] = col.z; }
@@ -1050,6 +1061,18 @@ static int march_rows_per_seg(int h, int w, int sm_count) {
   return best_rs;
 }
 
+// Function attributes are per device: called by b200vqa_create for the context's device (not behind a process-wide flag).
+int flow_init_device_attrs() {
+  VQA_CUDA(cudaFuncSetAttribute(k4_flow_iter, cudaFuncAttributeMaxDynamicSharedMemorySize, BX_SMEM));
+  VQA_CUDA(cudaFuncSetAttribute(k4_flow_iter_march<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MS_SMEM));
+  VQA_CUDA(cudaFuncSetAttribute(k4_flow_iter_march<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MS_SMEM));
+  VQA_CUDA(cudaFuncSetAttribute(k4_pyr_level<0, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+  VQA_CUDA(cudaFuncSetAttribute(k4_pyr_level<3, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+  VQA_CUDA(cudaFuncSetAttribute(k4_pyr_level<9, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+  VQA_CUDA(cudaFuncSetAttribute(k4_pyr_level<19, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+  return B200VQA_OK;
+}
+
 }  // namespace b200vqa
 
 using namespace b200vqa;
@@ -1074,17 +1097,6 @@ extern "C" int b200vqa_farneback(b200vqa_t* h, const uint8_t* gray0, const uint8
   float* flowB = flowA + 2 * (size_t)B * P;
   float* I = flowB + 2 * (size_t)B * P;
   static const PolyConsts pc = poly_consts();
-  static bool attr_done = false;
-  if (!attr_done) {
-    VQA_CUDA(cudaFuncSetAttribute(k4_flow_iter, cudaFuncAttributeMaxDynamicSharedMemorySize, BX_SMEM));
-    VQA_CUDA(cudaFuncSetAttribute(k4_flow_iter_march<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MS_SMEM));
-    VQA_CUDA(cudaFuncSetAttribute(k4_flow_iter_march<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MS_SMEM));
-    VQA_CUDA(cudaFuncSetAttribute(k4_pyr_level<0, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    VQA_CUDA(cudaFuncSetAttribute(k4_pyr_level<3, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    VQA_CUDA(cudaFuncSetAttribute(k4_pyr_level<9, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    VQA_CUDA(cudaFuncSetAttribute(k4_pyr_level<19, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    attr_done = true;
-  }
   static const bool poly_tile = getenv("B200VQA_POLY_TILE") != nullptr;      // A/B: 64 x 16 tile expansion kernel
   float* prev = nullptr;         // flow of the previous (coarser) level
   int ph = 0, pw = 0;

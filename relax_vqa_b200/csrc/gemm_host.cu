@@ -50,11 +50,6 @@ int launch_gemm(const CUtensorMap& map_a, const CUtensorMap& map_b, const GemmPa
   if (p.block_n % 16 || p.block_n < 16 || p.block_n > 256 || p.stages < 2 || p.stages > GEMM_MAX_STAGES) return B200VQA_EINVAL;
   size_t smem = gemm_smem_bytes(p.block_n, p.stages);
   if (smem > 227 * 1024) return B200VQA_EINVAL;
-  static bool attr_set = false;
-  if (!attr_set) {
-    VQA_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
-  }
   GemmParams q = p;
   if (const char* e = getenv("B200VQA_GEMM_STAGES")) { int v = atoi(e); if (v >= 2 && v <= GEMM_MAX_STAGES && gemm_smem_bytes(p.block_n, v) <= 227 * 1024) q.stages = v; }
   if (const char* e = getenv("B200VQA_GEMM_NOEPI")) q.dbg_skip_epilogue = atoi(e);
@@ -96,11 +91,6 @@ int launch_gemm_2cta(const CUtensorMap& map_a, const CUtensorMap& map_b, int M, 
   if (const char* e = getenv("B200VQA_GEMM_RASTER")) p.raster = atoi(e);
   p.act = act; p.M = M; p.N = N; p.ldo = N; p.out_is_f32 = out_is_f32; p.bias = bias; p.residual = residual; p.out = out;
   const size_t smem = (size_t)p.stages * G2_STAGE_BYTES + fixed;
-  static bool attr_set = false;
-  if (!attr_set) {
-    VQA_CUDA(cudaFuncSetAttribute(gemm2cta_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
-  }
   const int tiles = p.m2_tiles * p.n_tiles;
   int clusters = sm_count / 2;
   if (clusters > tiles) clusters = tiles;
@@ -119,6 +109,12 @@ int launch_gemm_2cta(const CUtensorMap& map_a, const CUtensorMap& map_b, int M, 
     ctx->prof_flops += 2.0 * M * (double)N * K;
   }
   VQA_LAUNCH_CHECK();
+  return B200VQA_OK;
+}
+
+int gemm_init_device_attrs() {
+  VQA_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  VQA_CUDA(cudaFuncSetAttribute(gemm2cta_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   return B200VQA_OK;
 }
 
@@ -169,7 +165,7 @@ extern "C" int b200vqa_gemm_f16(b200vqa_t* h, const void* A, const void* B, cons
     int rc2;
     if ((rc2 = make_tmap_f16(&ma2, A, 2, da2, sa2, box2, nullptr))) return rc2;
     if ((rc2 = make_tmap_f16(&mb2, B, 2, db2, sa2, box2, nullptr))) return rc2;
-    return launch_gemm_2cta(ma2, mb2, M, N, K, bias, nullptr, D, 1, ACT_NONE, h->sm_count, st);
+    return launch_gemm_2cta(ma2, mb2, M, N, K, bias, nullptr, D, 1, ACT_NONE, gemm_grid_sms(h), st);
   }
   int bn = N >= 256 ? 256 : ((N + 15) / 16) * 16;
   if (const char* e = getenv("B200VQA_GEMM_BN")) { int v = atoi(e); if (v >= 16 && v <= 256 && v % 16 == 0) bn = v; }
@@ -183,5 +179,5 @@ extern "C" int b200vqa_gemm_f16(b200vqa_t* h, const void* A, const void* B, cons
   p.m_tiles = cdiv(M, GEMM_BM); p.n_tiles = cdiv(N, bn); p.block_n = bn;
   p.k_blocks_per_tap = cdiv(K, GEMM_BK); p.taps_r = p.taps_s = 1; p.stages = pick_stages(bn);
   p.epi = EPI_ROW; p.act = ACT_NONE; p.M = M; p.N = N; p.ldo = N; p.out_is_f32 = 1; p.bias = bias; p.out = D;
-  return launch_gemm(ma, mb, p, h->sm_count, st);
+  return launch_gemm(ma, mb, p, gemm_grid_sms(h), st);
 }

@@ -28,6 +28,8 @@ struct Bottleneck { ConvW c1, c2, c3, ds; bool has_ds = false; };
 struct ResNetWeights {
   ConvW stem;
   __half* eye = nullptr;          // [128][128] one-hot A operand for the tensor-core residual add
+  float* ones64 = nullptr;        // scale / shift of the raw conv1 hook (b200vqa_resnet50_maps)
+  float* zeros64 = nullptr;
   CUtensorMap map_eye;
   std::vector<Bottleneck> blocks;
   std::vector<void*> allocs;
@@ -114,6 +116,23 @@ k8_maxpool(const __half* __restrict__ in, __half* __restrict__ out, int Nimg, in
     }
   }
   *reinterpret_cast<uint4*>(out + ((n * Hout + y) * Wout + x) * C + c8 * 8) = *reinterpret_cast<uint4*>(m);
+}
+
+// boundary-fidelity path (b200vqa_resnet50_maps): one hooked activation, fp16 NHWC -> fp32 CHW at `dst` of each image's record
+__global__ void __launch_bounds__(256)
+k8_dump_map(const __half* __restrict__ act, int HW, int C, float* __restrict__ maps, size_t per_img, size_t offset) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z, p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int r = ty; r < 32; r += 8) {
+    const int p = p0 + r, c = c0 + tx;
+    tile[r][tx] = (p < HW && c < C) ? __half2float(act[((size_t)n * HW + p) * C + c]) : 0.f;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int c = c0 + r, p = p0 + tx;
+    if (c < C && p < HW) maps[(size_t)n * per_img + offset + (size_t)c * HW + p] = tile[tx][r];
+  }
 }
 
 struct HookDesc { const float* partial; int tiles_y, C, offset; float inv_hw; };
@@ -277,9 +296,9 @@ static int run_conv(b200vqa_ctx* h, const ConvW& cw, const __half* in, int Nimg,
     uint64_t strides[3] = {(uint64_t)cw.Cout * 2, (uint64_t)Wout * cw.Cout * 2, (uint64_t)Hout * Wout * cw.Cout * 2};
     uint32_t box[4] = {GEMM_BK, (uint32_t)g.tw, (uint32_t)g.th, (uint32_t)g.tn};
     if ((rc = make_tmap_f16(&mi, identity, 4, dims, strides, box, nullptr))) return rc;
-    return launch_gemm(cw.map_a, mb, p, h->sm_count, st, &rw.map_eye, &mi);
+    return launch_gemm(cw.map_a, mb, p, gemm_grid_sms(h), st, &rw.map_eye, &mi);
   }
-  return launch_gemm(cw.map_a, mb, p, h->sm_count, st);
+  return launch_gemm(cw.map_a, mb, p, gemm_grid_sms(h), st);
 }
 
 static const int kStagePlanes[4] = {64, 128, 256, 512};
@@ -325,6 +344,9 @@ extern "C" int b200vqa_load_resnet50(b200vqa_t* h, int n, const char* const* nam
     uint64_t dims[2] = {128, 128}, strides[1] = {128 * 2};
     uint32_t box[2] = {GEMM_BK, GEMM_BM};
     if (!rc) rc = make_tmap_f16(&rw->map_eye, rw->eye, 2, dims, strides, box, nullptr);
+    const std::vector<float> one(64, 1.0f), zero(64, 0.0f);
+    if (!rc) rc = upload(rw, one.data(), 64 * sizeof(float), (void**)&rw->ones64);
+    if (!rc) rc = upload(rw, zero.data(), 64 * sizeof(float), (void**)&rw->zeros64);
   }
   if (rc) { free_resnet(rw); return rc; }
   free_resnet(h->resnet);
@@ -332,9 +354,10 @@ extern "C" int b200vqa_load_resnet50(b200vqa_t* h, int n, const char* const* nam
   return B200VQA_OK;
 }
 
-extern "C" int b200vqa_resnet50_features(b200vqa_t* h, const uint8_t* img, int B, int is_bgr, float* stack, float* pool,
-                                         void* stream) {
-  if (!h || !img || B <= 0 || (!stack && !pool)) return B200VQA_EINVAL;
+// maps: [B][B200VQA_RESNET_MAP_FLOATS] fp32, the 15 hooked activations of each image as (C,H,W) arrays in hook order, or null
+static int resnet_forward(b200vqa_t* h, const uint8_t* img, int B, int is_bgr, float* stack, float* pool, float* maps,
+                          void* stream) {
+  if (!h || !img || B <= 0 || (!stack && !pool && !maps)) return B200VQA_EINVAL;
   if (!h->resnet) return B200VQA_ENOTLOADED;
   CtxScope scope(h);
   cudaStream_t st = as_stream(stream);
@@ -375,6 +398,20 @@ extern "C" int b200vqa_resnet50_features(b200vqa_t* h, const uint8_t* img, int B
     k8_stem_im2col<<<(unsigned)((npix * 8 + 255) / 256), 256, 0, st>>>(im, is_bgr, col, npix);
     VQA_LAUNCH_CHECK();
     float* gp = add_hook(h->gemm_impl == 1 ? 1 : 56 * GEMM_EPI_GROUPS, 64, 12544);
+    size_t map_off = 0;
+    const size_t per_img = B200VQA_RESNET_MAP_FLOATS;
+    auto dump = [&](const __half* act, int HW, int C) {
+      k8_dump_map<<<dim3(cdiv(HW, 32), cdiv(C, 32), n), 256, 0, st>>>(act, HW, C, maps + (size_t)b0 * per_img, per_img, map_off);
+      count_launch();
+      map_off += (size_t)HW * C;
+    };
+    if (maps) {
+      // the conv1 hook is the raw convolution output (before bn1 / relu): one extra stem launch with scale 1, shift 0, no ReLU
+      ConvW raw = rw.stem;
+      raw.scale = rw.ones64; raw.shift = rw.zeros64;
+      if ((rc = run_conv(h, raw, col, n, 224, 224, c1, nullptr, 0, nullptr, 0, st))) return rc;
+      dump(c1, 12544, 64);
+    }
     if ((rc = run_conv(h, rw.stem, col, n, 224, 224, c1, nullptr, 1, gp, 1, st))) return rc;
     {
       const size_t total = (size_t)n * 56 * 56 * 8;
@@ -400,6 +437,7 @@ extern "C" int b200vqa_resnet50_features(b200vqa_t* h, const uint8_t* img, int B
           g = add_hook(h->gemm_impl == 1 ? 1 : cdiv(Ho, ge.th) * GEMM_EPI_GROUPS, bk.c3.Cout, Ho * Ho);
         }
         if ((rc = run_conv(h, bk.c3, bb, n, Ho, Ho, y, idt, 1, g, 0, st))) return rc;
+        if (maps && b < kStageHooks[s]) dump(y, Ho * Ho, bk.c3.Cout);
         __half* t = x; x = y; y = t;
         Hc = Ho;
       }
@@ -415,4 +453,15 @@ extern "C" int b200vqa_resnet50_features(b200vqa_t* h, const uint8_t* img, int B
     }
   }
   return B200VQA_OK;
+}
+
+extern "C" int b200vqa_resnet50_features(b200vqa_t* h, const uint8_t* img, int B, int is_bgr, float* stack, float* pool,
+                                         void* stream) {
+  if (!stack && !pool) return B200VQA_EINVAL;
+  return resnet_forward(h, img, B, is_bgr, stack, pool, nullptr, stream);
+}
+
+extern "C" int b200vqa_resnet50_maps(b200vqa_t* h, const uint8_t* img, int B, int is_bgr, float* maps, void* stream) {
+  if (!maps) return B200VQA_EINVAL;
+  return resnet_forward(h, img, B, is_bgr, nullptr, nullptr, maps, stream);
 }

@@ -305,6 +305,34 @@ k11_final_norm_pool(const float* __restrict__ x, const float* __restrict__ w, co
   o[c] = mean; o[VD + c] = mx; o[2 * VD + c] = sqrtf(sq / VP);
 }
 
+// final LayerNorm of the 196 patch tokens, un-pooled: what the reference's extract_features returns, norm(x)[:, 1:]
+// (visualise_vit_layer.py:234-239, :492-500).  Debug / boundary-fidelity path only (b200vqa_vitb16_tokens).
+__global__ void __launch_bounds__(256)
+k11_final_norm_tokens(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias, float* __restrict__ out, int nimg) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= nimg * VP) return;
+  const int b = row / VP, t = row - b * VP;
+  const float* xr = x + ((size_t)b * VT + 1 + t) * VD;
+  float v[24], s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 24; ++i) { v[i] = xr[lane + 32 * i]; s += v[i]; }
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / VD;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < 24; ++i) { const float d = v[i] - mean; q += d * d; }
+  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float rstd = rsqrtf(q / VD + 1e-6f);
+  float* orow = out + (size_t)row * VD;
+#pragma unroll
+  for (int i = 0; i < 24; ++i) { const int c = lane + 32 * i; orow[c] = (v[i] - mean) * rstd * w[c] + bias[c]; }
+}
+
+int vit_init_device_attrs() {
+  VQA_CUDA(cudaFuncSetAttribute(k10_attention, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
+  return B200VQA_OK;
+}
+
 // ------------------------------------------------------------------------- weight loading
 typedef std::map<std::string, std::pair<const float*, int64_t>> TensorMap;
 
@@ -347,7 +375,7 @@ static int run_linear(b200vqa_ctx* h, const Linear& lin, const __half* A, int M,
   int rc = make_tmap_f16(&ma, A, 2, dims, strides, box, nullptr);
   if (rc) return rc;
   if (h->gemm_impl == 0 && lin.N % 256 == 0 && lin.K % GEMM_BK == 0)      // default: SM-pair kernel (cta_group::2)
-    return launch_gemm_2cta(ma, lin.map_b128, M, lin.N, lin.K, lin.b, residual, out, out_is_f32, act, h->sm_count, st);
+    return launch_gemm_2cta(ma, lin.map_b128, M, lin.N, lin.K, lin.b, residual, out, out_is_f32, act, gemm_grid_sms(h), st);
   GemmParams p{};
   p.block_n = 256;
   p.m_tiles = cdiv(M, GEMM_BM); p.n_tiles = cdiv(lin.N, 256);
@@ -355,7 +383,7 @@ static int run_linear(b200vqa_ctx* h, const Linear& lin, const __half* A, int M,
   p.stages = pick_stages(256);
   p.epi = EPI_ROW; p.act = act; p.M = M; p.N = lin.N; p.ldo = lin.N; p.out_is_f32 = out_is_f32;
   p.bias = lin.b; p.residual = residual; p.out = out;
-  return launch_gemm(ma, lin.map_b, p, h->sm_count, st);
+  return launch_gemm(ma, lin.map_b, p, gemm_grid_sms(h), st);
 }
 
 }  // namespace b200vqa
@@ -392,17 +420,13 @@ extern "C" int b200vqa_load_vitb16(b200vqa_t* h, int n, const char* const* names
   return B200VQA_OK;
 }
 
-extern "C" int b200vqa_vitb16_features(b200vqa_t* h, const uint8_t* img, int B, int is_bgr, float* out, void* stream) {
-  if (!h || !img || !out || B <= 0) return B200VQA_EINVAL;
+// out: pooled [B][2304] or null; tokens: un-pooled final-LayerNorm patch tokens [B][196][768] or null
+static int vit_forward(b200vqa_t* h, const uint8_t* img, int B, int is_bgr, float* out, float* tokens, void* stream) {
+  if (!h || !img || (!out && !tokens) || B <= 0) return B200VQA_EINVAL;
   if (!h->vit) return B200VQA_ENOTLOADED;
   CtxScope scope(h);
   cudaStream_t st = as_stream(stream);
   const ViTWeights& vw = *h->vit;
-  static bool attr_done = false;
-  if (!attr_done) {
-    VQA_CUDA(cudaFuncSetAttribute(k10_attention, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
-    attr_done = true;
-  }
   // images per pass: as many as the workspace allows (512 images = 1.3 GB).  Each of the 49 tcgen05 launches of a pass
   // costs ~10 us of prologue / ramp / tail (tools/gemm_waves.py), and with >= 8 waves per launch the partial last wave
   // matters less than that fixed cost (a 264-image step: 9 / 25 / 34 waves for the 3 / 9 / 12 column tiles).
@@ -441,8 +465,24 @@ extern "C" int b200vqa_vitb16_features(b200vqa_t* h, const uint8_t* img, int B, 
       if ((rc = run_linear(h, bk.fc1, hbuf, m, big, 0, ACT_GELU, nullptr, st))) return rc;
       if ((rc = run_linear(h, bk.fc2, big, m, x, 1, ACT_NONE, x, st))) return rc;
     }
-    k11_final_norm_pool<<<n, 768, 0, st>>>(x, vw.norm_w, vw.norm_b, out + (size_t)b0 * B200VQA_VIT_POOL);
-    VQA_LAUNCH_CHECK();
+    if (out) {
+      k11_final_norm_pool<<<n, 768, 0, st>>>(x, vw.norm_w, vw.norm_b, out + (size_t)b0 * B200VQA_VIT_POOL);
+      VQA_LAUNCH_CHECK();
+    }
+    if (tokens) {
+      k11_final_norm_tokens<<<cdiv(n * VP, 8), 256, 0, st>>>(x, vw.norm_w, vw.norm_b, tokens + (size_t)b0 * VP * VD, n);
+      VQA_LAUNCH_CHECK();
+    }
   }
   return B200VQA_OK;
+}
+
+extern "C" int b200vqa_vitb16_features(b200vqa_t* h, const uint8_t* img, int B, int is_bgr, float* out, void* stream) {
+  if (!out) return B200VQA_EINVAL;
+  return vit_forward(h, img, B, is_bgr, out, nullptr, stream);
+}
+
+extern "C" int b200vqa_vitb16_tokens(b200vqa_t* h, const uint8_t* img, int B, int is_bgr, float* tokens, void* stream) {
+  if (!tokens) return B200VQA_EINVAL;
+  return vit_forward(h, img, B, is_bgr, nullptr, tokens, stream);
 }

@@ -23,15 +23,33 @@ def _sorted_frames(folder, video_name):
     return orig, nxt
 
 
-def load_clip(sampled_frame_path, sampled_fragment_path, video_name, device):
+def load_clip_host(sampled_frame_path, sampled_fragment_path, video_name, pin=False):
+    """-> (frames [Tf,H,W,3], nexts [Tp,H,W,3]) uint8 BGR host tensors (pinned on request) from the reference's PNG layout."""
     full, _ = _sorted_frames(sampled_frame_path, video_name)
     orig, nxt = _sorted_frames(sampled_fragment_path, video_name)
+    if not full:
+        raise FileNotFoundError(f"no sampled frames {video_name}_*.png in {sampled_frame_path}")
     n = min(len(orig), len(nxt))
-    rd = lambda ps: torch.from_numpy(np.stack([cv2.imread(p) for p in ps])).to(device)
+
+    def rd(ps, like=None):
+        imgs = [cv2.imread(p) for p in ps]
+        if any(i is None for i in imgs):
+            raise ValueError("unreadable PNG among " + ", ".join(os.path.basename(p) for p in ps[:3]))
+        if not imgs:
+            return torch.empty((0,) + tuple(like.shape[1:]), dtype=torch.uint8)
+        t = torch.from_numpy(np.stack(imgs))
+        return t.pin_memory() if pin and torch.cuda.is_available() else t
+
     # the full-frame blocks average over all sampled frames, the fragment blocks over pairs (ref :80-87, :104)
     if [os.path.basename(p) for p in full[:n]] != [os.path.basename(p) for p in orig[:n]]:
         raise ValueError("sampled-frame and fragment folders disagree")
-    return Clip(rd(full), rd(nxt[:n]))
+    frames = rd(full)
+    return frames, rd(nxt[:n], like=frames)
+
+
+def load_clip(sampled_frame_path, sampled_fragment_path, video_name, device):
+    frames, nexts = load_clip_host(sampled_frame_path, sampled_fragment_path, video_name)
+    return Clip(frames.to(device), nexts.to(device))
 
 
 def evaluate_video_quality(config):

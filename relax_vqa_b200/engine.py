@@ -54,12 +54,18 @@ class Clip:
 
 class Engine:
     def __init__(self, device=0, resnet_sd=None, vit_sd=None, head_sd=None, imputer_mean=None, scaler_scale=None,
-                 scaler_min=None, seed_if_missing=True):
+                 scaler_min=None, seed_if_missing=False):
+        """seed_if_missing=True (bench / tests / smoke only) substitutes seeded synthetic backbones for missing state
+        dicts; by default a missing backbone is an error, as features from random weights are meaningless."""
+        if (resnet_sd is None or vit_sd is None) and not seed_if_missing:
+            raise ops._lib.B200VQAError("weights not loaded (B200VQA_ENOTLOADED): Engine needs resnet_sd and vit_sd "
+                                        "(seed_if_missing=True substitutes seeded synthetic weights)")
         self.ctx = ops.Context(device)
         self.device = self.ctx.device
-        if resnet_sd is None and seed_if_missing:
+        self.synthetic_weights = resnet_sd is None or vit_sd is None
+        if resnet_sd is None:
             resnet_sd = weights.seeded_resnet50_state_dict()
-        if vit_sd is None and seed_if_missing:
+        if vit_sd is None:
             vit_sd = weights.seeded_vitb16_state_dict()
         ops.load_resnet50(self.ctx, resnet_sd)
         ops.load_vitb16(self.ctx, vit_sd)
@@ -104,6 +110,21 @@ class Engine:
     #: False = everything on the current stream, one clip after the other (clean per-kernel timings for profiling)
     concurrent = True
 
+    #: True = software pipeline across calls: the image stages (HBM-bound) of a call depend only on their clips being
+    #: ready, not on the previous call's backbones (tensor-bound), so the lanes run one call ahead of the backbone streams
+    #: and the two phases share the GPU instead of alternating.  False = every call starts after the previous one ended.
+    pipeline = True
+
+    #: SMs the persistent tcgen05 grids may occupy (0 = all 148); the rest stays free for the lanes' kernels
+    gemm_sms = 0
+
+    def set_gemm_sms(self, sms):
+        self.gemm_sms = int(sms)
+        self.ctx.set_gemm_sms(self.gemm_sms)
+
+    def flow_kernel_name(self):
+        return "k4_flow_iter_march"
+
     @property
     def launches(self):
         """Kernels launched by this engine (all lanes)."""
@@ -136,10 +157,17 @@ class Engine:
         lanes = self._lanes() if self.concurrent else [(main, ctx)]
         full_rn, full_vt, oris, mers = [], [], [], []
         full_off, pair_off = [0], [0]
-        for s, _ in lanes[:len(clips)]:
-            s.wait_stream(main)
+        piped = self.concurrent and self.pipeline
+        if not piped:
+            for s, _ in lanes[:len(clips)]:
+                s.wait_stream(main)
         for i, c in enumerate(clips):
             s, lctx = lanes[i % len(lanes)]
+            if piped and c.ready is None:
+                # first use of this clip: everything queued on the current stream so far (its producer) is the dependency;
+                # later calls with the same (immutable) clip find the event complete and do not wait for earlier backbones
+                c.ready = torch.cuda.Event()
+                c.ready.record(main)
             with torch.cuda.stream(s):
                 if c.ready is not None:
                     s.wait_event(c.ready)

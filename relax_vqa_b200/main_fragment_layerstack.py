@@ -32,7 +32,14 @@ def extract_important_patches(residual_frame, diff, patch_size=16, target_size=2
     """ref :191-210 -> (fragment (224,224,3) uint8, positions list[(y, x)] in raster order)."""
     _require_patch16(patch_size, target_size, top_n)
     img = runtime.to_dev(residual_frame[None])
-    sums = runtime.to_dev(np.asarray(diff)[None].astype(np.int32))
+    d = np.asarray(diff, dtype=np.float64)
+    if d.size and np.all(d >= 0) and np.all(d == np.floor(d)) and d.max() < 2 ** 31:
+        keys = d.astype(np.int32)                      # what get_patch_diff returns: exact integer sums
+    else:
+        # any other float map (the reference accepts one): dense ranks keep the order and the ties of the values,
+        # so the kernel's (value desc, index asc) rule picks what np.argsort(-diff, kind="stable") picks
+        keys = np.unique(d, return_inverse=True)[1].reshape(d.shape).astype(np.int32)
+    sums = runtime.to_dev(keys[None])
     pos, cnt = ops.topk_patches(sums)
     frag, _ = ops.gather_fragments(img, None, pos, cnt, want_ori=True, want_diff=False)
     k = int(cnt[0])
@@ -102,13 +109,28 @@ def _vit_input(img_bgr):
 
 
 def get_deep_feature(network_name, video_name, image_path, qp, layer_name):
-    """ref :83-121.  Returns (png_path, npy_path, frame_feature).  frame_feature is the already-pooled
-    vector for this image (PooledFrame): (13120,) for resnet50/layer_stack, (2048,) for resnet50/pool,
-    (2304,) for vit - process_video_feature below consumes it and yields the reference's (T, D) rows."""
+    """ref :83-121.  Returns (png_path, npy_path, frame_feature).
+
+    Default (fast path): frame_feature is the already-pooled vector for this image (PooledFrame): (13120,) for
+    resnet50/layer_stack, (2048,) for resnet50/pool, (2304,) for vit.
+    With runtime.configure(return_maps=True) it has the reference's own types: dict[layer name -> (C,H,W) float32] for
+    resnet50/layer_stack, (2048,1,1) for resnet50/pool, (196,768) for vit.
+    process_video_feature below consumes either and yields the reference's (T, D) rows."""
     png_path = f'../visualisation/{network_name}/{video_name}/'
     npy_path = f'../features/{network_name}/{video_name}/'
     eng = runtime.engine()
     img = _load_bgr(image_path)
+    if runtime.return_maps():
+        if network_name == 'resnet50':
+            maps = ops.resnet50_maps(eng.ctx, _resnet_input(img), is_bgr=True)
+            if layer_name == 'layer_stack':
+                return png_path, npy_path, {name: m[0].cpu().numpy() for name, m in zip(RESNET_LAYERS, maps)}
+            if layer_name == 'pool':
+                # the avgpool hook (visualise_resnet_layer.py:62-102): spatial mean of layer4[2]'s output
+                return png_path, npy_path, maps[-1][0].mean(dim=(1, 2)).reshape(2048, 1, 1).cpu().numpy()
+        elif network_name == 'vit':
+            return png_path, npy_path, ops.vitb16_tokens(eng.ctx, _vit_input(img), is_bgr=True)[0].cpu().numpy()
+        raise ValueError(f"unsupported network/layer on the B200 hot path: {network_name}/{layer_name}")
     if network_name == 'resnet50':
         stack, pool = ops.resnet50_features(eng.ctx, _resnet_input(img), is_bgr=True, want_stack=True, want_pool=True)
         if layer_name == 'layer_stack':
@@ -122,13 +144,17 @@ def get_deep_feature(network_name, video_name, image_path, qp, layer_name):
 
 
 def process_video_feature(video_feature, network_name, layer_name):
-    """ref :124-160 -> (T, 13120) for 'layer_stack', (T, 2051) for 'pool'."""
+    """ref :124-160 -> (T, 13120) for 'layer_stack', (T, 2051) for 'pool'.  Each element of `video_feature` is what
+    get_deep_feature returned: a PooledFrame (fast path) or the reference's raw type (return_maps=True), pooled here
+    the way the reference pools it (per-layer np.mean over (H, W), :131-140; hstack of [v, mean, max, std], :141-149)."""
     rows = []
     for frame in video_feature:
-        v = np.asarray(frame, dtype=np.float32)
         if layer_name == 'layer_stack':
-            rows.append(v)
+            if isinstance(frame, dict):
+                rows.append(np.concatenate([np.mean(np.asarray(a, dtype=np.float32), axis=(1, 2)) for a in frame.values()]))
+            else:
+                rows.append(np.asarray(frame, dtype=np.float32))
         else:
-            v = np.squeeze(v)
+            v = np.squeeze(np.asarray(frame, dtype=np.float32))
             rows.append(np.hstack([v, np.mean(v, axis=0), np.max(v, axis=0), np.std(v, axis=0)]).astype(np.float32))
     return np.array(rows)

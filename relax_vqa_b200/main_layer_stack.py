@@ -2,6 +2,7 @@
 import numpy as np
 
 from . import main_fragment_layerstack as _mfl
+from .main_fragment_pool import pool_vit_tokens
 
 
 def get_deep_feature(network_name, video_name, image_path, qp):
@@ -11,5 +12,8 @@ def get_deep_feature(network_name, video_name, image_path, qp):
 
 
 def process_video_feature(video_feature, network_name):
-    """ref :115-151 -> (T, 13120) for resnet50, (T, 2304) for vit."""
-    return np.array([np.asarray(f, dtype=np.float32) for f in video_feature])
+    """ref :115-151 -> (T, 13120) for resnet50 (per-layer spatial mean, :138), (T, 2304) for vit (:126-131).
+    Accepts pooled vectors (fast path) and the reference's raw maps / tokens (return_maps=True)."""
+    if network_name == 'resnet50':
+        return _mfl.process_video_feature(video_feature, network_name, 'layer_stack')
+    return np.array([pool_vit_tokens(f) for f in video_feature])

@@ -60,6 +60,10 @@ class Context:
     def set_flow_impl(self, impl):
         check(self.lib.b200vqa_set_flow_impl(self.h, int(impl)), "set_flow_impl")
 
+    def set_gemm_sms(self, sms):
+        """Persistent tcgen05 grids use at most `sms` SMs (0 = all): room for concurrent bandwidth kernels."""
+        check(self.lib.b200vqa_set_gemm_sms(self.h, int(sms)), "set_gemm_sms")
+
     def set_gemm_impl(self, impl):
         check(self.lib.b200vqa_set_gemm_impl(self.h, int(impl)), "set_gemm_impl")
 
@@ -218,6 +222,31 @@ def vitb16_features(ctx, img, is_bgr=True):
     B = _u8(img).shape[0]
     out = torch.empty((B, 2304), dtype=torch.float32, device=img.device)
     check(ctx.lib.b200vqa_vitb16_features(ctx.h, ptr(img), B, int(is_bgr), ptr(out), stream_ptr(img.device)), "vitb16_features")
+    return out
+
+
+RESNET_MAP_SHAPES = [(64, 112, 112)] + [(256, 56, 56)] * 3 + [(512, 28, 28)] * 4 + [(1024, 14, 14)] * 4 + [(2048, 7, 7)] * 3
+RESNET_MAP_FLOATS = sum(c * h * w for c, h, w in RESNET_MAP_SHAPES)
+
+
+def resnet50_maps(ctx, img, is_bgr=True):
+    """img [B,224,224,3] u8 -> list of 15 fp32 tensors [B,C,H,W]: the raw hooked activations the reference's
+    visualise_resnet.process_video_frame returns (boundary-fidelity path; the fast path pools in the conv epilogues)."""
+    B = _u8(img).shape[0]
+    flat = torch.empty((B, RESNET_MAP_FLOATS), dtype=torch.float32, device=img.device)
+    check(ctx.lib.b200vqa_resnet50_maps(ctx.h, ptr(img), B, int(is_bgr), ptr(flat), stream_ptr(img.device)), "resnet50_maps")
+    out, o = [], 0
+    for c, h, w in RESNET_MAP_SHAPES:
+        out.append(flat[:, o:o + c * h * w].reshape(B, c, h, w))
+        o += c * h * w
+    return out
+
+
+def vitb16_tokens(ctx, img, is_bgr=True):
+    """img [B,224,224,3] u8 -> final-LayerNorm patch tokens [B,196,768] fp32 (norm(x)[:, 1:], visualise_vit_layer.py:234-239)."""
+    B = _u8(img).shape[0]
+    out = torch.empty((B, 196, 768), dtype=torch.float32, device=img.device)
+    check(ctx.lib.b200vqa_vitb16_tokens(ctx.h, ptr(img), B, int(is_bgr), ptr(out), stream_ptr(img.device)), "vitb16_tokens")
     return out
 
 

@@ -131,3 +131,72 @@ def test_reference_golden_video_blocks(ctx, golden_dir):
     vit = ops.vitb16_features(ctx, vt_in, is_bgr=True)
     assert max(seg_err(stack.cpu().numpy(), g["full_resnet"], SEGMENTS)) <= 1e-2
     assert max(seg_err(vit.cpu().numpy(), g["full_vit"], [768, 768, 768])) <= 1e-2
+
+
+def _many_images(n, seed=5):
+    """n distinct 224x224 BGR images: smooth synthetic frames, their rolls / flips, and white noise."""
+    fr, nx = synth.make_clip(seed, 224, 224, 12)
+    base = np.concatenate([fr, nx])                                        # 24 images
+    rng = np.random.default_rng(seed)
+    out = []
+    for i in range(n):
+        b = base[i % len(base)]
+        k = i // len(base)
+        if k % 4 == 1:
+            b = np.roll(b, (7 * k, 13 * k), axis=(0, 1))
+        elif k % 4 == 2:
+            b = b[::-1, :, ::-1]
+        elif k % 4 == 3:
+            b = rng.integers(0, 256, b.shape, dtype=np.uint8)
+        out.append(np.ascontiguousarray(b))
+    return np.stack(out)
+
+
+def test_backbones_at_the_bench_shape(ctx):
+    """parity at the batch the 1080p benchmark runs (4 clips x 66 = 264 images per pass: 204 row-tile
+    pairs, 26 raster groups, 9/25/34 waves) - tcgen05 vs the SIMT check path on all rows, 8 sampled rows vs the fp32
+    oracle, and batch invariance against single-image calls."""
+    from relax_vqa_b200 import ops
+    rsd, vsd = weights.seeded_resnet50_state_dict(1234), weights.seeded_vitb16_state_dict(4321)
+    images = _many_images(264)
+    dev = torch.from_numpy(images).cuda()
+    ctx.set_gemm_impl(1)
+    chk_stack, chk_pool = ops.resnet50_features(ctx, dev, want_stack=True, want_pool=True)
+    chk_vit = ops.vitb16_features(ctx, dev)
+    ctx.set_gemm_impl(0)
+    stack, pool = ops.resnet50_features(ctx, dev, want_stack=True, want_pool=True)
+    vit = ops.vitb16_features(ctx, dev)
+    torch.cuda.synchronize()
+    e_rn = seg_err(stack.cpu().numpy(), chk_stack.cpu().numpy(), SEGMENTS)
+    e_vt = seg_err(vit.cpu().numpy(), chk_vit.cpu().numpy(), [768] * 3)
+    print("264 images, tcgen05 vs SIMT check: resnet", max(e_rn), "vit", max(e_vt))
+    assert max(e_rn) < 2e-3 and max(e_vt) < 3e-3
+    assert max(seg_err(pool.cpu().numpy(), chk_pool.cpu().numpy(), [2048, 1, 1, 1])) < 2e-3
+    rows = [0, 1, 37, 100, 131, 200, 262, 263]
+    x = OB.resnet_preprocess(images[rows][..., ::-1])
+    assert max(seg_err(stack[rows].cpu().numpy(), OB.resnet50_layerstack(rsd, x), SEGMENTS)) <= 1e-2
+    assert max(seg_err(pool[rows].cpu().numpy(), OB.resnet50_pool(rsd, x), [2048, 1, 1, 1])) <= 1e-2
+    assert max(seg_err(vit[rows].cpu().numpy(), OB.vit_pool(vsd, OB.vit_preprocess(images[rows][..., ::-1])), [768] * 3)) <= 1e-2
+    for r in (0, 131, 263):                                                # batch invariance against B = 1, bit for bit
+        one_s, one_p = ops.resnet50_features(ctx, dev[r:r + 1].contiguous(), want_stack=True, want_pool=True)
+        assert torch.equal(one_s[0], stack[r]) and torch.equal(one_p[0], pool[r])
+        assert torch.equal(ops.vitb16_features(ctx, dev[r:r + 1].contiguous())[0], vit[r])
+
+
+def test_backbones_split_passes_above_512_images(ctx):
+    """B = 520 executes the > 512-image split (two balanced passes of 260): every row equals the row of a smaller batch,
+    bit for bit, and sampled rows match the fp32 oracle."""
+    from relax_vqa_b200 import ops
+    rsd, vsd = weights.seeded_resnet50_state_dict(1234), weights.seeded_vitb16_state_dict(4321)
+    images = _many_images(520, seed=6)
+    dev = torch.from_numpy(images).cuda()
+    stack, pool = ops.resnet50_features(ctx, dev, want_stack=True, want_pool=True)
+    vit = ops.vitb16_features(ctx, dev)
+    for lo, hi in ((0, 7), (255, 265), (513, 520)):                        # windows that straddle the pass boundary (260) and the ends
+        s2, p2 = ops.resnet50_features(ctx, dev[lo:hi].contiguous(), want_stack=True, want_pool=True)
+        assert torch.equal(s2, stack[lo:hi]) and torch.equal(p2, pool[lo:hi])
+        assert torch.equal(ops.vitb16_features(ctx, dev[lo:hi].contiguous()), vit[lo:hi])
+    rows = [0, 259, 260, 519]
+    x = OB.resnet_preprocess(images[rows][..., ::-1])
+    assert max(seg_err(stack[rows].cpu().numpy(), OB.resnet50_layerstack(rsd, x), SEGMENTS)) <= 1e-2
+    assert max(seg_err(vit[rows].cpu().numpy(), OB.vit_pool(vsd, OB.vit_preprocess(images[rows][..., ::-1])), [768] * 3)) <= 1e-2

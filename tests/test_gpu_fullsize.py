@@ -16,7 +16,7 @@ pytestmark = pytest.mark.gpu
 @pytest.fixture(scope="module")
 def engine():
     from relax_vqa_b200.engine import Engine
-    e = Engine(0, head_sd=weights.seeded_head_state_dict())
+    e = Engine(0, head_sd=weights.seeded_head_state_dict(), seed_if_missing=True)
     yield e
     e.close()
 

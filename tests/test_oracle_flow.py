@@ -43,13 +43,38 @@ def test_pyramid_plan():
     assert len(FB.pyramid_plan(100, 150)) == 2      # 25x37 < 32 stops the pyramid early
 
 
-def test_flow_to_rgb_vs_cv2():
-    fr, nx = synth.make_clip(5, 272, 480, 1)
+@pytest.mark.parametrize("hw,seed", [((272, 480), 5), ((544, 960), 6), ((128, 256), 7)])
+def test_flow_to_rgb_vs_cv2(hw, seed):
+    """Widths that are multiples of cv2's SIMD width: the whole colouring (magnitude, both normalize passes, hue,
+    HSV2BGR) is bit-exact up to the 1-ulp differences of cv2's vectorised fastAtan2 (< 1e-5 of the pixels)."""
+    fr, nx = synth.make_clip(seed, hw[0], hw[1], 1)
     flow = _cv_flow(F.bgr2gray(fr[0]), F.bgr2gray(nx[0]))
     got, ref = FB.flow_to_rgb(flow), _cv_flow_to_rgb(flow)
     bad = (got != ref).any(-1)
-    # cv2's scalar row-tail path rounds instead of truncating: allow +-1 on a few px
-    assert bad.mean() < 1e-3 and np.abs(got.astype(int) - ref.astype(int)).max() <= 1
+    assert bad.mean() < 1e-5, bad.sum()
+
+
+def test_flow_to_rgb_vs_cv2_ragged_width():
+    # cv2's scalar row-tail path rounds instead of truncating (SURVEY.md 8(a) A6): +-1 on the last < 32 px of a row
+    rng = np.random.default_rng(0)
+    flow = (rng.standard_normal((123, 211, 2)) * 2).astype(np.float32)
+    got, ref = FB.flow_to_rgb(flow), _cv_flow_to_rgb(flow)
+    bad = (got != ref).any(-1)
+    assert not bad[:, :211 - 32].any() and np.abs(got.astype(int) - ref.astype(int)).max() <= 1
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_normalize_twice_is_cv2_exact(seed):
+    """The reference normalises the magnitude twice (src/main_fragment_layerstack.py:164,172); the float32 restatement
+    of cv2.normalize and of cartToPolar's magnitude is bit-identical to cv2 for both passes."""
+    rng = np.random.default_rng(seed)
+    flow = (rng.standard_normal((97, 161, 2)) * rng.uniform(0.05, 8)).astype(np.float32)
+    mag, _ = cv2.cartToPolar(flow[..., 0], flow[..., 1])
+    assert np.array_equal(FB.cv_magnitude(flow[..., 0], flow[..., 1]), mag)
+    m1 = cv2.normalize(mag, None, 0, 255, cv2.NORM_MINMAX)
+    m2 = cv2.normalize(m1, None, 0, 255, cv2.NORM_MINMAX)
+    assert np.array_equal(FB._cv_normalize_minmax_255(mag), m1)
+    assert np.array_equal(FB._cv_normalize_minmax_255(m1), m2)
 
 
 @pytest.mark.parametrize("idx", [2, 3])

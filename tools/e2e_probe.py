@@ -8,7 +8,7 @@ if os.environ.get("BIND"):
     print("bound to", len(bind_host_to_gpu(0) or []), "cpus of", os.cpu_count(), flush=True)
 
 H, W, PAIRS, CLIPS, STEPS = 1080, 1920, 22, 4, 8
-eng = Engine(0, head_sd=weights.seeded_head_state_dict())
+eng = Engine(0, head_sd=weights.seeded_head_state_dict(), seed_if_missing=True)
 clips = synthetic_clips_on_device(CLIPS, H, W, PAIRS, eng.device, seed=1)
 host = [(c.frames.cpu().pin_memory(), c.nexts.cpu().pin_memory()) for c in clips]
 nbytes = sum(f.numel() + n.numel() for f, n in host)

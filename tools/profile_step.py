@@ -18,7 +18,7 @@ ap.add_argument("--pairs", type=int, default=22)
 ap.add_argument("--steps", type=int, default=1)
 ap.add_argument("--warmup", type=int, default=2)
 a = ap.parse_args()
-eng = Engine(0, head_sd=weights.seeded_head_state_dict())
+eng = Engine(0, head_sd=weights.seeded_head_state_dict(), seed_if_missing=True)
 clips = synthetic_clips_on_device(a.clips, a.height, a.width, a.pairs, eng.device, seed=5)
 for _ in range(a.warmup):
     eng.predict(clips, "live_vqc")

@@ -5,7 +5,7 @@ import torch
 from relax_vqa_b200 import weights
 from relax_vqa_b200.engine import Engine, synthetic_clips_on_device
 
-eng = Engine(0, head_sd=weights.seeded_head_state_dict())
+eng = Engine(0, head_sd=weights.seeded_head_state_dict(), seed_if_missing=True)
 for name, (H, W, pairs, n) in {"540p-8s": (540, 960, 18, 8), "2160p-20s": (2160, 3840, 43, 1), "portrait-720x404": (720, 404, 10, 2)}.items():
     clips = synthetic_clips_on_device(n, H, W, pairs, eng.device, seed=3)
     for _ in range(2):

@@ -5,7 +5,7 @@ import numpy as np, torch
 from relax_vqa_b200 import synth, weights
 from relax_vqa_b200.engine import Clip, Engine
 
-eng = Engine(0, head_sd=weights.seeded_head_state_dict())
+eng = Engine(0, head_sd=weights.seeded_head_state_dict(), seed_if_missing=True)
 for hw in ((144, 256), (100, 150)):
     fr, nx = synth.make_clip(1, hw[0], hw[1], 2)
     feats, score = eng.predict([Clip(torch.from_numpy(fr).cuda(), torch.from_numpy(nx).cuda())], "konvid_1k")

@@ -166,6 +166,9 @@ int64_t b200vqa_launch_count(b200vqa_t* h);
 /* debug switch: 0 = tcgen05 (default; linear layers on the 2-CTA cta_group::2 kernel), 1 = SIMT check kernels for
  * every GEMM/conv, 2 = tcgen05 with the 1-CTA kernel everywhere (A/B measurements) */
 int b200vqa_set_gemm_impl(b200vqa_t* h, int impl);
+/* debug switch for the ViT attention (A/B measurements): 0 = tcgen05 / TMEM kernel (default: S = QK^T and O = PV on the 5th-gen
+ * tensor cores, P kept in tensor memory), 1 = the warp-level mma.sync kernel of round 1 */
+int b200vqa_set_attn_impl(b200vqa_t* h, int impl);
 /* scheduling knob: persistent tcgen05 GEMM / conv grids of this context occupy at most `sms` SMs (even; 0 = all), leaving
  * the rest of the GPU to kernels running concurrently on other streams (the bandwidth stages of the next batch).  Results
  * do not depend on it (tiles are computed identically whichever CTA takes them). */

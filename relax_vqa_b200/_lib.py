@@ -43,6 +43,7 @@ SIGNATURES = {
     "b200vqa_gemm_f16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "b200vqa_launch_count": (c_int64, [c_void_p]),
     "b200vqa_set_gemm_impl": (c_int, [c_void_p, c_int]),
+    "b200vqa_set_attn_impl": (c_int, [c_void_p, c_int]),
     "b200vqa_set_gemm_sms": (c_int, [c_void_p, c_int]),
     "b200vqa_set_profiling": (c_int, [c_void_p, c_int]),
     "b200vqa_set_flow_impl": (c_int, [c_void_p, c_int]),

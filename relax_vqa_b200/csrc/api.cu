@@ -86,6 +86,12 @@ extern "C" int b200vqa_set_gemm_impl(b200vqa_t* h, int impl) {
   return B200VQA_OK;
 }
 
+extern "C" int b200vqa_set_attn_impl(b200vqa_t* h, int impl) {
+  if (!h || impl < 0 || impl > 1) return B200VQA_EINVAL;
+  h->attn_impl = impl;
+  return B200VQA_OK;
+}
+
 extern "C" int b200vqa_set_gemm_sms(b200vqa_t* h, int sms) {
   if (!h || sms < 0 || (sms & 1)) return B200VQA_EINVAL;
   h->gemm_sms = sms;

@@ -239,6 +239,229 @@ k10_attention(const __half* __restrict__ qkv, __half* __restrict__ out, float sc
   }
 }
 
+// ---- fused attention on the 5th-generation tensor cores (tcgen05 + TMEM), the default path.
+//   reference op: Attention.forward, src/extractor/visualise_vit_layer.py:93-106 (q k^T * scale, softmax, @ v).
+// One work item = one (image, head): Q, K, V are 197 x 64 fp16 slices of the qkv buffer, fetched by TMA (SWIZZLE_128B)
+// as two 128-row query tiles and 208-row K / V tiles (rows past the image belong to the next image or are zero-filled
+// past the end of the buffer: their scores are masked, their outputs never stored).  Per query tile:
+//   S = Q K^T      tcgen05.mma kind::f16, M = 128, N = 208, K = 64: A and B K-major from shared memory -> TMEM cols [0, 208)
+//   softmax        two threads per row (TMEM lane): warp set A takes keys [0, 112), set B keys [112, 208); two tcgen05.ld sweeps
+//                  (row max; exp2 / row sum) with the next chunk's load in flight, partial max / sum exchanged through shared
+//                  memory.  P goes back to TENSOR MEMORY as packed fp16: set A over the S columns it has consumed
+//                  (cols [0, 56)), set B into the free columns [208, 256)
+//   O = P V        tcgen05.mma with the A operand in tensor memory and V as an MN-major shared-memory operand (the
+//                  [key][dim] tile TMA delivers IS the canonical MN-major SW128 layout), M = 128, N = 64, K = 208 -> cols [128, 192)
+//   O / rowsum     tcgen05.ld, fp16, 32-byte vector stores (each warp set writes 64 bytes of the row).
+// A CTA owns 256 TMEM columns and one shared-memory stage (84 KB; Q / K are refilled as soon as the second S has retired,
+// V when the second P V has): two CTAs per SM alternate, one in its softmax (XU-bound: 197 x 208 exponentials per item)
+// while the other multiplies.
+constexpr int ATC_SM_WARPS = 8;                            // softmax / epilogue warps: two per TMEM lane quadrant
+constexpr int ATC_THREADS = 64 + 32 * ATC_SM_WARPS;        // warp 0: TMA producer, warp 1: TMEM allocator + MMA issuer
+constexpr int ATC_KV_ROWS = 208, ATC_SPLIT = 112;          // keys [0, 112) -> warp set A, [112, 208) -> set B
+constexpr uint32_t ATC_Q_BYTES = 128 * VHD * 2, ATC_KV_BYTES = ATC_KV_ROWS * VHD * 2;
+constexpr uint32_t ATC_STAGE_BYTES = 2 * ATC_Q_BYTES + 2 * ATC_KV_BYTES;          // 86,016
+constexpr uint32_t ATC_TMEM_COLS = 256, ATC_O_COL = 128, ATC_PB_COL = 208;
+constexpr int ATC_SMEM = ATC_STAGE_BYTES + 2 * 2 * 128 * 4 + 8 * 8 + 16 + 1024;
+
+__device__ __forceinline__ void tcgen05_mma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ void named_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+
+__global__ void __launch_bounds__(ATC_THREADS, 2)
+k10_attention_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv, __half* __restrict__ out,
+                 int nimg, float scale) {
+  extern __shared__ __align__(1024) uint8_t atc_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(atc_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sQ0 = smem; uint8_t* sQ1 = smem + ATC_Q_BYTES; uint8_t* sK = smem + 2 * ATC_Q_BYTES; uint8_t* sV = sK + ATC_KV_BYTES;
+  float* s_max = reinterpret_cast<float*>(smem + ATC_STAGE_BYTES);            // [2][128] partial row maxima of the two warp sets
+  float* s_sum = s_max + 256;                                                  // [2][128] partial row sums
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_sum + 256);
+  uint64_t* full_qk = bars; uint64_t* full_v = bars + 1; uint64_t* free_qk = bars + 2; uint64_t* free_v = bars + 3;
+  uint64_t* s_full = bars + 4; uint64_t* p_full = bars + 5; uint64_t* o_full = bars + 6; uint64_t* s_free = bars + 7;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_q) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_kv) : "memory");
+    mbar_init(full_qk, 1); mbar_init(full_v, 1); mbar_init(free_qk, 1); mbar_init(free_v, 1);
+    mbar_init(s_full, 1); mbar_init(p_full, ATC_SM_WARPS); mbar_init(o_full, 1); mbar_init(s_free, ATC_SM_WARPS);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(ATC_TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int items = nimg * VH;
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    if (lane == 0) {
+      int it = 0;
+      for (int item = blockIdx.x; item < items; item += gridDim.x, ++it) {
+        const int b = item / VH, hh = item - b * VH;
+        const uint32_t par = (uint32_t)(it & 1);
+        mbar_wait(free_qk, par ^ 1u);                                         // both S products of the previous item have retired
+        mbar_expect_tx(full_qk, 2 * ATC_Q_BYTES + ATC_KV_BYTES);
+        tma_load_2d(&map_q, full_qk, sQ0, hh * VHD, b * VT);
+        tma_load_2d(&map_q, full_qk, sQ1, hh * VHD, b * VT + 128);
+        tma_load_2d(&map_kv, full_qk, sK, VD + hh * VHD, b * VT);
+        mbar_wait(free_v, par ^ 1u);                                          // ... and its second P V
+        mbar_expect_tx(full_v, ATC_KV_BYTES);
+        tma_load_2d(&map_kv, full_v, sV, 2 * VD + hh * VHD, b * VT);
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ==================================
+    if (lane == 0) {
+      const uint32_t idesc_s = make_idesc(ATC_KV_ROWS);                      // A, B K-major
+      const uint32_t idesc_o = make_idesc(VHD) | (1u << 16);                  // B (V) MN-major
+      const uint64_t dK = make_smem_desc(smem_u32(sK)), dV = make_smem_desc(smem_u32(sV));
+      const uint64_t dQ0 = make_smem_desc(smem_u32(sQ0)), dQ1 = make_smem_desc(smem_u32(sQ1));
+      int it = 0;
+      for (int item = blockIdx.x; item < items; item += gridDim.x, ++it) {
+        const uint32_t par = (uint32_t)(it & 1);
+        mbar_wait(full_qk, par);
+        tcgen05_fence_after();
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          const uint32_t n = (uint32_t)(2 * it + t);
+          const uint64_t dQ = t ? dQ1 : dQ0;
+          mbar_wait(s_free, (n & 1u) ^ 1u);                                   // the previous tile's O has been read out of the region
+          tcgen05_fence_after();
+#pragma unroll
+          for (int k = 0; k < VHD / 16; ++k)                                  // +32 B per K = 16 step inside the swizzled row
+            tcgen05_mma_f16(tmem_base, dQ + (uint64_t)(2 * k), dK + (uint64_t)(2 * k), idesc_s, k != 0);
+          tcgen05_commit(s_full);
+          if (t == 1) tcgen05_commit(free_qk);                                // Q / K of the next item may land
+          mbar_wait(p_full, n & 1u);
+          if (t == 0) mbar_wait(full_v, par);
+          tcgen05_fence_after();
+#pragma unroll
+          for (int k = 0; k < ATC_KV_ROWS / 16; ++k) {                        // 16 keys = 8 TMEM columns of packed fp16 = 2048 B of V
+            const uint32_t pcol = k < ATC_SPLIT / 16 ? (uint32_t)(8 * k) : ATC_PB_COL + (uint32_t)(8 * (k - ATC_SPLIT / 16));
+            tcgen05_mma_f16_ts(tmem_base + ATC_O_COL, tmem_base + pcol, dV + (uint64_t)(128 * k), idesc_o, k != 0);
+          }
+          tcgen05_commit(o_full);
+          if (t == 1) tcgen05_commit(free_v);
+        }
+      }
+    }
+  } else {
+    // ================================ softmax / epilogue ==========================
+    const int q = warp & 3;                                                   // TMEM lane quadrant of this warp
+    const int half = (warp - 2) >> 2;                                         // 0: keys [0, 112) (set A), 1: keys [112, 208) (set B)
+    const int rl = q * 32 + lane;                                             // row inside the tile = TMEM lane
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+    const int col0 = half ? ATC_SPLIT : 0, nchunk = half ? (ATC_KV_ROWS - ATC_SPLIT) / 16 : ATC_SPLIT / 16;
+    const uint32_t pcol0 = half ? ATC_PB_COL : 0u;
+    const float sl2 = scale * 1.4426950408889634f;
+    int it = 0;
+    for (int item = blockIdx.x; item < items; item += gridDim.x, ++it) {
+      const int b = item / VH, hh = item - b * VH;
+#pragma unroll 1
+      for (int t = 0; t < 2; ++t) {
+        const uint32_t n = (uint32_t)(2 * it + t);
+        const int row = t * 128 + rl;
+        const bool warp_valid = t * 128 + q * 32 < VT;                        // warp-uniform
+        mbar_wait(s_full, n & 1u);
+        tcgen05_fence_after();
+        float m = -INFINITY;
+        if (warp_valid) {
+          uint32_t v[2][16];
+          tmem_ld16(taddr + col0, v[0]);
+#pragma unroll
+          for (int c = 0; c < 7; ++c) {
+            if (c < nchunk) {
+              tmem_ld_wait();
+              if (c + 1 < nchunk) tmem_ld16(taddr + col0 + 16 * (c + 1), v[(c + 1) & 1]);
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (col0 + 16 * c + j < VT) m = fmaxf(m, __uint_as_float(v[c & 1][j]));
+            }
+          }
+          s_max[half * 128 + rl] = m;
+        }
+        named_bar_sync(1, 32 * ATC_SM_WARPS);
+        float inv_l = 0.f;
+        if (warp_valid) {
+          m = fmaxf(m, s_max[(half ^ 1) * 128 + rl]);
+          const float mk = m * sl2;
+          float l = 0.f;
+          uint32_t v[2][16];
+          tmem_ld16(taddr + col0, v[0]);
+#pragma unroll
+          for (int c = 0; c < 7; ++c) {
+            if (c < nchunk) {
+              tmem_ld_wait();
+              if (c + 1 < nchunk) tmem_ld16(taddr + col0 + 16 * (c + 1), v[(c + 1) & 1]);
+              uint32_t pk[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const int k0 = col0 + 16 * c + 2 * j;
+                const float p0 = k0 < VT ? ex2_approx(fmaf(__uint_as_float(v[c & 1][2 * j]), sl2, -mk)) : 0.f;
+                const float p1 = k0 + 1 < VT ? ex2_approx(fmaf(__uint_as_float(v[c & 1][2 * j + 1]), sl2, -mk)) : 0.f;
+                l += p0 + p1;
+                pk[j] = pack_h2(p0, p1);
+              }
+              tmem_st8(taddr + pcol0 + 8 * c, pk);                           // set A: over S columns it has already consumed
+            }
+          }
+          tmem_st_wait();
+          s_sum[half * 128 + rl] = l;
+        }
+        tcgen05_fence_before();
+        named_bar_sync(2, 32 * ATC_SM_WARPS);
+        if (lane == 0) mbar_arrive(p_full);
+        if (warp_valid) inv_l = 1.0f / (s_sum[rl] + s_sum[128 + rl]);
+        mbar_wait(o_full, n & 1u);
+        tcgen05_fence_after();
+        if (warp_valid) {
+          uint32_t o[32];
+          tmem_ld32(taddr + ATC_O_COL + 32 * half, o);
+          tmem_ld_wait();
+          if (row < VT) {
+            __half* op = out + ((size_t)b * VT + row) * VD + hh * VHD + 32 * half;
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+              uint32_t h8[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                h8[j] = pack_h2(__uint_as_float(o[16 * i + 2 * j]) * inv_l, __uint_as_float(o[16 * i + 2 * j + 1]) * inv_l);
+              asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(op + 16 * i), "r"(h8[0]), "r"(h8[1]), "r"(h8[2]),
+                           "r"(h8[3]), "r"(h8[4]), "r"(h8[5]), "r"(h8[6]), "r"(h8[7]) : "memory");
+            }
+          }
+        }
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(s_free);
+      }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ATC_TMEM_COLS) : "memory");
+  }
+}
+
 // SIMT check version of the attention (one thread per (query, head-dim) output)
 __global__ void ref_attention(const __half* __restrict__ qkv, __half* __restrict__ out, float scale) {
   const int hh = blockIdx.x, b = blockIdx.y, q = blockIdx.z;
@@ -330,6 +553,7 @@ k11_final_norm_tokens(const float* __restrict__ x, const float* __restrict__ w, 
 
 int vit_init_device_attrs() {
   VQA_CUDA(cudaFuncSetAttribute(k10_attention, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
+  VQA_CUDA(cudaFuncSetAttribute(k10_attention_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC_SMEM));
   return B200VQA_OK;
 }
 
@@ -457,7 +681,17 @@ static int vit_forward(b200vqa_t* h, const uint8_t* img, int B, int is_bgr, floa
       VQA_LAUNCH_CHECK();
       if ((rc = run_linear(h, bk.qkv, hbuf, m, big, 0, ACT_NONE, nullptr, st))) return rc;
       if (h->gemm_impl == 1) ref_attention<<<dim3(VH, n, VT), 64, 0, st>>>(big, att, 0.125f);
-      else k10_attention<<<dim3(VH, n), AT_WARPS * 32, AT_SMEM, st>>>(big, att, 0.125f);
+      else if (h->attn_impl == 1) k10_attention<<<dim3(VH, n), AT_WARPS * 32, AT_SMEM, st>>>(big, att, 0.125f);
+      else {
+        // Q / K / V are column slices of the qkv buffer [m][2304]: one descriptor with 128-row boxes, one with 208-row boxes
+        CUtensorMap mq, mkv;
+        uint64_t dims[2] = {(uint64_t)(3 * VD), (uint64_t)m}, strides[1] = {(uint64_t)(3 * VD) * 2};
+        uint32_t boxq[2] = {VHD, 128}, boxkv[2] = {VHD, ATC_KV_ROWS};
+        if ((rc = make_tmap_f16(&mq, big, 2, dims, strides, boxq, nullptr))) return rc;
+        if ((rc = make_tmap_f16(&mkv, big, 2, dims, strides, boxkv, nullptr))) return rc;
+        const int items = n * VH, grid = items < 2 * h->sm_count ? items : 2 * h->sm_count;
+        k10_attention_tc<<<grid, ATC_THREADS, ATC_SMEM, st>>>(mq, mkv, att, n, 0.125f);
+      }
       VQA_LAUNCH_CHECK();
       if ((rc = run_linear(h, bk.proj, att, m, x, 1, ACT_NONE, x, st))) return rc;
       k11_layernorm<<<cdiv(m, 8), 256, 0, st>>>(x, bk.ln2_w, bk.ln2_b, hbuf, m);

@@ -113,7 +113,10 @@ class Engine:
     #: True = software pipeline across calls: the image stages (HBM-bound) of a call depend only on their clips being
     #: ready, not on the previous call's backbones (tensor-bound), so the lanes run one call ahead of the backbone streams
     #: and the two phases share the GPU instead of alternating.  False = every call starts after the previous one ended.
-    pipeline = True
+    #: Measured on the 1080p workload (profiles/r2_overlap_sweep.log): 93.0 videos/s piped vs 97.6 un-piped, for every
+    #: gemm_sms setting - both phases are bound by per-SM resources (issue slots / shared memory / tensor pipe), so sharing
+    #: the SMs adds no throughput and the interleaving costs the persistent GEMM grids their wave structure.  Off by default.
+    pipeline = False
 
     #: SMs the persistent tcgen05 grids may occupy (0 = all 148); the rest stays free for the lanes' kernels
     gemm_sms = 0

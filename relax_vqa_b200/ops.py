@@ -60,6 +60,9 @@ class Context:
     def set_flow_impl(self, impl):
         check(self.lib.b200vqa_set_flow_impl(self.h, int(impl)), "set_flow_impl")
 
+    def set_attn_impl(self, impl):
+        check(self.lib.b200vqa_set_attn_impl(self.h, int(impl)), "set_attn_impl")
+
     def set_gemm_sms(self, sms):
         """Persistent tcgen05 grids use at most `sms` SMs (0 = all): room for concurrent bandwidth kernels."""
         check(self.lib.b200vqa_set_gemm_sms(self.h, int(sms)), "set_gemm_sms")

@@ -101,7 +101,7 @@ def test_fragments_vs_oracle_and_reference(engine, golden_dir):
         print(f"pair {t}: merged-fragment pixel mismatch rate {mism:.5f}, flow patch-set symmetric difference {pos_sym}")
         _record("merged_fragment_vs_reference", dict(pair=t, pixel_mismatch_rate=float(mism), flow_patch_set_symmetric_difference=int(pos_sym),
                                                       flow_max_abs_err_px_vs_fp16_golden=float(flow_err.max())))
-        assert mism < 0.02 and pos_sym <= 4
+        assert mism < 2e-3 and pos_sym <= 2          # observed r2 (cv2-exact colouring): <= 4e-5 and 0, profiles/r2_parity_observed.jsonl
 
 
 def test_multi_clip_batch_equals_single(engine):
@@ -244,36 +244,76 @@ def test_srcc_and_mos_parity_over_several_videos(golden_dir):
 
 def test_srcc_540p_32_clips(golden_dir):
     """the SRCC / MOS acceptance on a BASELINE config's resolution - 32 distinct 540p clips (2 sampled
-    pairs each, content scaled so the scores spread), GPU vs the CPU oracle with shared seeded weights."""
+    pairs each), GPU vs the CPU oracle (cv2 Farneback, the reference's own flow) with shared seeded weights.  The head's
+    BatchNorm statistics are calibrated on these clips (as training would) so that the scores spread over several MOS
+    points and feature errors are amplified, not hidden behind a near-constant output.
+    Segments that do not depend on the optical flow must agree within 1e-2 on every clip; the two merged-fragment blocks
+    (flow-dependent top-196 selection: a tolerance-class stage) must agree within 1e-2 on every clip
+    whose flow patch set equals cv2's, and the clips where it differs are counted and reported."""
+    import cv2 as _cv2
     import scipy.stats
     from relax_vqa_b200.engine import Clip, Engine
     s = np.load(os.path.join(golden_dir, "konvid_1k_scaler_imputer.npz"))
     rsd, vsd = weights.seeded_resnet50_state_dict(1234), weights.seeded_vitb16_state_dict(4321)
-    hsd = weights.seeded_head_state_dict(99, swa_format=True)
-    eng = Engine(0, rsd, vsd, hsd, s["imputer_mean"], s["scale"], s["minv"])
-    clips, frames = [], []
+    flow = lambda a, b: _cv2.calcOpticalFlowFarneback(a, b, None, 0.5, 3, 15, 3, 5, 1.2, 0)
+    frames, vecs, ref_flow_pos = [], [], []
     for i in range(32):
         fr, nx = synth.make_clip(900 + i, 540, 960, 2)
-        gain = 0.35 + 0.04 * i
-        fr = np.clip((fr.astype(np.float32) - 128) * gain + 128 - 40 + 2.5 * i, 0, 255).astype(np.uint8)
-        nx = np.clip((nx.astype(np.float32) - 128) * gain + 128 - 40 + 2.5 * i, 0, 255).astype(np.uint8)
+        # diverse content so that the scores are well separated: contrast, brightness, blur, colour cast, inversion
+        gain = 0.25 + 0.05 * i
+        cast = np.array([1.0, 1.0 - 0.02 * (i % 7), 1.0 - 0.03 * (i % 5)], np.float32)
+        def style(a):
+            a = (a.astype(np.float32) - 128) * gain + 128 - 50 + 3.0 * i
+            if i % 3 == 1:
+                a = np.stack([_cv2.GaussianBlur(x, (0, 0), 1.0 + 0.15 * i) for x in a])
+            if i % 4 == 3:
+                a = 255.0 - a
+            return np.clip(a * cast, 0, 255).astype(np.uint8)
+        fr, nx = style(fr), style(nx)
         frames.append((fr, nx))
-        clips.append(Clip(torch.from_numpy(fr).cuda(), torch.from_numpy(nx).cuda()))
+        blocks = P.video_feature_blocks(fr, nx, rsd, vsd, flow_fn=flow)
+        vecs.append(P.video_vector(blocks))
+        ref_flow_pos.append([set(map(tuple, p["flow_positions"])) for p in blocks["pairs"]])
+    vecs = np.stack(vecs)
+    # calibrated head: BN running statistics = statistics of fc1's outputs over these clips
+    hsd = weights.seeded_head_state_dict(99)
+    x = OH_impute(vecs, s)
+    h = x.astype(np.float32) @ hsd["fc1.weight"].numpy().T + hsd["fc1.bias"].numpy()
+    hsd["bn1.running_mean"] = torch.from_numpy(h.mean(0).astype(np.float32))
+    hsd["bn1.running_var"] = torch.from_numpy(h.var(0).astype(np.float32) + 1e-6)
+    hsd["fc3.weight"] = hsd["fc3.weight"] * 4.0                          # spread the outputs over several MOS points
+    ref = np.array([P.predict(v, hsd, s["imputer_mean"], s["scale"], s["minv"], "konvid_1k") for v in vecs])
+    eng = Engine(0, rsd, vsd, hsd, s["imputer_mean"], s["scale"], s["minv"])
+    clips = [Clip(torch.from_numpy(fr).cuda(), torch.from_numpy(nx).cuda()) for fr, nx in frames]
     feats, score = eng.predict(clips, "konvid_1k")
-    got = score.cpu().numpy()
-    gf = feats.cpu().numpy()
-    import cv2 as _cv2
-    flow = lambda a, b: _cv2.calcOpticalFlowFarneback(a, b, None, 0.5, 3, 15, 3, 5, 1.2, 0)        # the reference's own flow
-    ref, worst = [], 0.0
-    for i, (fr, nx) in enumerate(frames):
-        vec = P.video_vector(P.video_feature_blocks(fr, nx, rsd, vsd, flow_fn=flow))
-        worst = max(worst, max(seg_err(gf[i], vec[None], VEC_SEGS)))
-        ref.append(P.predict(vec, weights.fix_state_dict(hsd), s["imputer_mean"], s["scale"], s["minv"], "konvid_1k"))
-    ref = np.array(ref)
+    got, gf = score.cpu().numpy(), feats.cpu().numpy()
+    # flow-dependent segments: frag_pool (2048 + 3 after the 15 frag_stack segments) and frag_vit_mer (last 3 x 768)
+    n_seg = len(VEC_SEGS)
+    flow_dep = set(range(15 + 3 + 15, 15 + 3 + 17)) | set(range(n_seg - 3, n_seg))
+    worst_indep, worst_dep_same, differing = 0.0, 0.0, 0
+    for i, c in enumerate(clips):
+        e = seg_err(gf[i], vecs[i][None], VEC_SEGS)
+        inter = eng.fragments(c.frames, c.nexts, keep_intermediates=True)
+        same = all(set(map(tuple, inter["flow_positions"][t].cpu().numpy().tolist())) == ref_flow_pos[i][t] for t in range(2))
+        worst_indep = max(worst_indep, max(v for k, v in enumerate(e) if k not in flow_dep))
+        if same:
+            worst_dep_same = max(worst_dep_same, max(e[k] for k in flow_dep))
+        else:
+            differing += 1
     srcc = scipy.stats.spearmanr(got, ref).correlation
-    print("540p x32: max |dMOS|", np.abs(got - ref).max(), "SRCC", srcc, "score range", ref.min(), ref.max(), "worst seg err", worst)
-    _record("srcc_540p_32_clips", dict(max_abs_dmos=float(np.abs(got - ref).max()), srcc=float(srcc), worst_feature_seg_err=float(worst),
+    print("540p x32: max |dMOS|", np.abs(got - ref).max(), "SRCC", srcc, "score range", ref.min(), ref.max(), "worst seg err: flow-independent",
+          worst_indep, "flow-dependent (same patch set)", worst_dep_same, "clips whose flow patch set differs from cv2's:", differing)
+    _record("srcc_540p_32_clips", dict(max_abs_dmos=float(np.abs(got - ref).max()), srcc=float(srcc), worst_seg_err_flow_independent=float(worst_indep),
+                                        worst_seg_err_flow_dependent_same_patches=float(worst_dep_same), clips_with_different_flow_patch_set=differing,
                                         score_min=float(ref.min()), score_max=float(ref.max())))
-    assert len(np.unique(np.round(ref, 3))) >= 30                         # a ranking test needs distinct scores
-    assert np.abs(got - ref).max() <= 0.01 and srcc >= 0.999 and worst <= 1e-2
+    gaps = np.diff(np.sort(ref))
+    print("score gaps between neighbours: median", np.median(gaps), "min", gaps.min())
+    assert ref.max() - ref.min() > 0.5 and np.median(gaps) > 5e-3      # a ranking test needs distinct, spread scores
+    assert worst_indep <= 1e-2 and worst_dep_same <= 1e-2 and differing <= 8
+    assert np.abs(got - ref).max() <= 0.01 and srcc >= 0.999
     eng.close()
+
+
+def OH_impute(x, s):
+    from oracle import head as OH
+    return OH.impute_scale(x, s["imputer_mean"], s["scale"], s["minv"])

@@ -1,45 +1,55 @@
-"""Attribute ncu SASS-level counters to CUDA source lines (nvdisasm -g line info joined by instruction order).
+"""Per-source-line attribution of an `ncu --set full --import-source on` capture: warp instructions, stall samples and the
+dominant stall reasons of each CUDA source line (ncu's own source correlation, `--print-source cuda,sass`).
 
-  python tools/sass_lines.py <report.ncu-rep> <mangled-kernel-substring> <source.cu> [cubin-name-substring]
+  python tools/sass_lines.py <report.ncu-rep> [--top 30] [ncu filter options, e.g. --kernel-name regex:k4_flow --launch-count 1]
 """
-import csv, os, re, subprocess, sys, tempfile
+import csv
+import os
+import subprocess
+import sys
 from collections import defaultdict
 
-rep, sym, src_path = sys.argv[1:4]
-lib = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "relax_vqa_b200", "lib", "libb200vqa.so")
-tmp = tempfile.mkdtemp()
-subprocess.run(["cuobjdump", "-xelf", "all", lib], cwd=tmp, capture_output=True)
-seq = None
-for f in sorted(os.listdir(tmp)):
-    dis = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, f)], capture_output=True, text=True).stdout.split("\n")
-    start = next((i for i, l in enumerate(dis) if l.startswith(".text.") and sym in l), None)
-    if start is None:
-        continue
-    cur, seq = None, []
-    for l in dis[start + 1:]:
-        if l.startswith("//---------------------"):
-            break
-        m = re.search(r'//## File "([^"]+)", line (\d+)', l)
-        if m:
-            cur = int(m.group(2)) if os.path.basename(m.group(1)) == os.path.basename(src_path) else -1
-            continue
-        if re.match(r"\s+/\*[0-9a-f]{4}\*/", l):
-            seq.append(cur)
-    break
-# reports with several kernels: pass e.g. "--kernel-name regex:k5_flow --launch-count 1" after the three positional arguments
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--print-source", "sass", "--csv"] + sys.argv[4:], capture_output=True, text=True).stdout
+args = sys.argv[1:]
+rep = args.pop(0)
+top = 30
+if "--top" in args:
+    i = args.index("--top")
+    top = int(args[i + 1])
+    del args[i:i + 2]
+out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--print-source", "cuda,sass", "--csv"] + args,
+                     capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
-hdr, data = rows[1], rows[2:]
-if seq is not None and len(data) > len(seq):      # several launches of the kernel in the report: keep the first
-    data = data[:len(seq)]
-iI, iS = hdr.index("Instructions Executed"), hdr.index("# Samples")
-assert seq is not None and len(seq) == len(data), (None if seq is None else len(seq), len(data))
-by = defaultdict(lambda: [0.0, 0.0])
-for k in range(len(data)):
-    by[seq[k]][0] += float(data[k][iI]); by[seq[k]][1] += float(data[k][iS])
-tot, tots = sum(v[0] for v in by.values()), sum(v[1] for v in by.values())
-src = open(src_path).read().split("\n")
-print(f"total warp instructions {tot:.0f}, stall samples {tots:.0f}")
-for ln, (a, b) in sorted(by.items(), key=lambda kv: -kv[1][0])[:32]:
-    s = src[ln - 1].strip()[:100] if ln and ln > 0 else "(other file / no line info)"
-    print(f"{a / tot * 100:5.1f}% instr {b / tots * 100:5.1f}% stall  L{ln}: {s}")
+lines = defaultdict(lambda: defaultdict(float))
+text = {}
+fname, hdr, kernel = None, None, None
+for r in rows:
+    if not r:
+        continue
+    if r[0] == "File Path":
+        fname = os.path.basename(r[1])
+    elif r[0] == "Function Name":
+        kernel = r[1]
+    elif r[0] == "Line No":
+        hdr = r
+    elif hdr and r[0].strip().isdigit() and len(r) == len(hdr):
+        key = (fname, int(r[0]))
+        text[key] = r[1].strip()
+        for name, val in zip(hdr[4:], r[4:]):
+            try:
+                lines[key][name] += float(val)
+            except ValueError:
+                pass
+tot_i = sum(v["Instructions Executed"] for v in lines.values()) or 1.0
+tot_s = sum(v["# Samples"] for v in lines.values()) or 1.0
+stall_cols = [c for c in (hdr or []) if c.startswith("stall_") and "Not Issued" not in c]
+print(f"kernel: {kernel}")
+print(f"total warp instructions {tot_i:.0f}, stall samples {tot_s:.0f}")
+agg = defaultdict(float)
+for v in lines.values():
+    for c in stall_cols:
+        agg[c] += v[c]
+print("stall mix: " + ", ".join(f"{c[6:]} {agg[c] / tot_s * 100:.1f}%" for c in sorted(stall_cols, key=lambda c: -agg[c])[:8]))
+for key, v in sorted(lines.items(), key=lambda kv: -kv[1]["# Samples"])[:top]:
+    why = sorted(stall_cols, key=lambda c: -v[c])[:2]
+    why = ", ".join(f"{c[6:]} {v[c] / max(v['# Samples'], 1) * 100:.0f}%" for c in why if v[c] > 0)
+    print(f"{v['Instructions Executed'] / tot_i * 100:5.1f}% instr {v['# Samples'] / tot_s * 100:5.1f}% samples  {key[0]}:{key[1]}  [{why}]  {text[key][:90]}")

@@ -56,6 +56,13 @@ const char* b200vqa_last_error(void);
 int b200vqa_create(int device, b200vqa_t** out);
 int b200vqa_destroy(b200vqa_t* h);
 
+/* ---- frame sampling from raw yuv420p (upstream of A1): the colour conversion ffmpeg / libswscale applies
+ * to the frames selected by extract_frames_yuv / extract_frames_residual_yuv (video_frames_extract.py:29-49, :76-100) before
+ * they are written as PNG: unscaled yuv420p -> bgr24, BT.601 limited range, chroma not interpolated, 16-bit fixed point
+ * (bit-identical to swscale's x86 path).  yuv: [B] frames of H*W luma bytes + two (H/2)*(W/2) chroma planes, densely packed;
+ * bgr: [B][H][W][3].  W % 4 == 0, H even. */
+int b200vqa_yuv420p_to_bgr(const uint8_t* yuv, int B, int H, int W, uint8_t* bgr, void* stream);
+
 /* ---- A1+A2 (+gray of A5): cv2.absdiff (main_fragment_layerstack.py:302), get_patch_diff
  * (:177-189), cv2.cvtColor BGR2GRAY (:313-314).  frame/next: [B][H][W][3] BGR.
  * sums: [B][H/16][W/16] exact uint32 patch sums of |next-frame| over 3 channels.

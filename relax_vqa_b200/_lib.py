@@ -22,6 +22,7 @@ SIGNATURES = {
     "b200vqa_last_error": (C.c_char_p, []),
     "b200vqa_create": (c_int, [c_int, C.POINTER(c_void_p)]),
     "b200vqa_destroy": (c_int, [c_void_p]),
+    "b200vqa_yuv420p_to_bgr": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "b200vqa_absdiff_patchsum_u8": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "b200vqa_patchsum_u8": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "b200vqa_topk_patches": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),

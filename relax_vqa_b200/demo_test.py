@@ -1,7 +1,8 @@
-"""Drop-in for src/demo_test.py::evaluate_video_quality on pre-sampled frames.
+"""Drop-in for src/demo_test.py::evaluate_video_quality.
 
-Frame sampling (ffmpeg, src/extractor/vf_extract.py) is upstream of the hot path:
-this entry point reads the PNGs the reference's sampler would have written."""
+With ``config['video_path']`` the video itself is sampled (video_frames_extract.sample_clip: raw yuv420p converted on the
+GPU, containers decoded by OpenCV's FFmpeg) and goes straight into the engine; without it the entry point reads the PNGs
+the reference's sampler has written under ``sampled_root`` (src/demo_test.py:68-69)."""
 import glob
 import os
 
@@ -57,8 +58,13 @@ def evaluate_video_quality(config):
     eng = runtime.engine()
     video_type, video_name = config['video_type'], config['video_name']
     save_path = config['save_path']
-    base = config.get('sampled_root', "../video_sampled_frame/original_sampled_frame/")
-    clip = load_clip(os.path.join(base, "test_sampled_frames"), os.path.join(base, "test_sampled_fragment"), video_name, eng.device)
+    if config.get('video_path'):
+        from .video_frames_extract import sample_clip
+        clip = sample_clip(video_type, config['video_path'], int(config['framerate'] / 2), config.get('video_width'),
+                           config.get('video_height'), config.get('pixfmt', 'yuv420p'), eng.device)        # ref :76, :92
+    else:
+        base = config.get('sampled_root', "../video_sampled_frame/original_sampled_frame/")
+        clip = load_clip(os.path.join(base, "test_sampled_frames"), os.path.join(base, "test_sampled_fragment"), video_name, eng.device)
     imputer = load(f'{save_path}/scaler/{video_type}_imputer.pkl')
     scaler = load(f'{save_path}/scaler/{video_type}_scaler.pkl')
     if config['is_finetune'] is True:

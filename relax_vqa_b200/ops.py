@@ -76,6 +76,16 @@ def _u8(t):
     return t
 
 
+def yuv420p_to_bgr(yuv, H, W):
+    """yuv [B, H*W*3/2] u8 (planar yuv420p frames) -> [B,H,W,3] u8 BGR: swscale's unscaled BT.601 conversion, bit-exact."""
+    lib = _lib.load()
+    B = _u8(yuv).shape[0]
+    assert yuv.shape[1] == H * W * 3 // 2
+    bgr = torch.empty((B, H, W, 3), dtype=torch.uint8, device=yuv.device)
+    check(lib.b200vqa_yuv420p_to_bgr(ptr(yuv), B, H, W, ptr(bgr), stream_ptr(yuv.device)), "yuv420p_to_bgr")
+    return bgr
+
+
 def absdiff_patchsum(frame, nxt, want_residual=False, want_gray=True):
     """frame/nxt [B,H,W,3] u8 BGR -> dict(sums [B,gh,gw] int32-valued uint32 bits, residual, gray0, gray1)."""
     lib = _lib.load()

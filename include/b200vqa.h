@@ -163,6 +163,31 @@ int b200vqa_temporal_mean_concat(const float* full_stack, const float* full_vit,
 /* ---- A17+A18: imputer + scaler + Mlp.forward (eval).  features [V][35203] -> score [V] */
 int b200vqa_head_forward(b200vqa_t* h, const float* features, int V, float* score, void* stream);
 
+/* ---- training of the Mlp head on the device (fp32), the arithmetic of the reference's loop
+ * (model_regression.py:292-306 train_one_epoch, :61-89 MAEAndRankLoss, :375-405 SGD momentum + weight decay / AveragedModel,
+ * :454-459 update_bn; fine_tune.py:130-193).  The schedule (epochs, cosine LR, SWA start, k-fold, early stopping) stays on the
+ * host: relax_vqa_b200/model_regression.py.  h_* = host float32 arrays in state-dict layout; X / y / masks / loss = device.
+ * `which`: 0 = the model being trained, 1 = its SWA average (AveragedModel: parameters averaged, buffers copied at creation). */
+typedef struct b200vqa_trainer b200vqa_trainer_t;
+int b200vqa_trainer_create(b200vqa_t* h, int in_features, int hidden, b200vqa_trainer_t** out);
+int b200vqa_trainer_destroy(b200vqa_trainer_t* t);
+int b200vqa_trainer_set_params(b200vqa_trainer_t* t, const float* h_fc1_w, const float* h_fc1_b, const float* h_bn_w, const float* h_bn_b,
+                               const float* h_bn_mean, const float* h_bn_var, const float* h_fc2_w, const float* h_fc2_b,
+                               const float* h_fc3_w, const float* h_fc3_b);
+int b200vqa_trainer_get_params(b200vqa_trainer_t* t, int which, float* h_fc1_w, float* h_fc1_b, float* h_bn_w, float* h_bn_b,
+                               float* h_bn_mean, float* h_bn_var, float* h_fc2_w, float* h_fc2_b, float* h_fc3_w, float* h_fc3_b);
+/* one optimisation step on a batch X [B][in], y [B] (B >= 2): train-mode forward (batch statistics, running statistics updated
+ * with momentum 0.1), MAE + rank loss, backward, SGD.  drop1 [B][hidden] / drop2 [B][hidden/2]: keep masks (1 = keep) of the two
+ * Dropout layers, ignored when drop_rate == 0.  loss_out: device float (may be NULL). */
+int b200vqa_trainer_step(b200vqa_trainer_t* t, const float* X, const float* y, int B, const uint8_t* drop1, const uint8_t* drop2,
+                         float drop_rate, float lr, float momentum, float weight_decay, float l1_w, float rank_w, float* loss_out,
+                         void* stream);
+int b200vqa_trainer_swa_update(b200vqa_trainer_t* t, void* stream);
+/* eval-mode forward (running statistics, no dropout): pred [B] device */
+int b200vqa_trainer_predict(b200vqa_trainer_t* t, int which, const float* X, int B, float* pred, void* stream);
+/* torch.optim.swa_utils.update_bn, one batch: batch_index 0 restarts the cumulative average of the batch statistics */
+int b200vqa_trainer_update_bn(b200vqa_trainer_t* t, int which, const float* X, int B, int batch_index, void* stream);
+
 /* ---- building blocks exposed for tests / profiling ------------------------------------ */
 /* D[M][N] = A[M][K] * B[N][K]^T (+bias[N]) on tcgen05; A, B fp16 row-major; D fp32. impl: 0
  * tcgen05 1-CTA kernel, 1 SIMT check kernel, 2 tcgen05 2-CTA (cta_group::2) kernel (N % 256 == 0, K % 64 == 0). */

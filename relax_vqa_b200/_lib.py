@@ -41,6 +41,14 @@ SIGNATURES = {
     "b200vqa_vitb16_tokens": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "b200vqa_temporal_mean_concat": (c_int, [c_void_p] * 8 + [c_int, c_void_p, c_void_p]),
     "b200vqa_head_forward": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
+    "b200vqa_trainer_create": (c_int, [c_void_p, c_int, c_int, C.POINTER(c_void_p)]),
+    "b200vqa_trainer_destroy": (c_int, [c_void_p]),
+    "b200vqa_trainer_set_params": (c_int, [c_void_p] + [c_void_p] * 10),
+    "b200vqa_trainer_get_params": (c_int, [c_void_p, c_int] + [c_void_p] * 10),
+    "b200vqa_trainer_step": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p] + [C.c_float] * 6 + [c_void_p, c_void_p]),
+    "b200vqa_trainer_swa_update": (c_int, [c_void_p, c_void_p]),
+    "b200vqa_trainer_predict": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p]),
+    "b200vqa_trainer_update_bn": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_void_p]),
     "b200vqa_gemm_f16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "b200vqa_launch_count": (c_int64, [c_void_p]),
     "b200vqa_set_gemm_impl": (c_int, [c_void_p, c_int]),

@@ -17,7 +17,11 @@ pytestmark = pytest.mark.gpu
 
 def _write_yuv(path, H, W, n, seed=3):
     """n frames of a drifting synthetic texture as planar yuv420p (converted with cv2: any legal planes will do)."""
-    fr, nx = synth.make_clip(seed, H, W, 2)
+    if H >= 64:
+        fr, nx = synth.make_clip(seed, H, W, 2)
+    else:                                                   # too small for the synthetic clip generator: noise
+        rng = np.random.default_rng(seed)
+        fr, nx = rng.integers(0, 256, (2, 2, H, W, 3), dtype=np.uint8)
     frames = []
     with open(path, "wb") as f:
         for i in range(n):

@@ -99,7 +99,7 @@ extern "C" int b200vqa_set_gemm_sms(b200vqa_t* h, int sms) {
 }
 
 extern "C" int b200vqa_set_flow_impl(b200vqa_t* h, int impl) {
-  if (!h || impl < 0 || impl > 2) return B200VQA_EINVAL;
+  if (!h || impl < 0 || impl > 3) return B200VQA_EINVAL;
   h->flow_impl = impl;
   return B200VQA_OK;
 }

@@ -578,22 +578,26 @@ k4_flow_iter(const float4* __restrict__ RA0, const float* __restrict__ RB0, cons
 // (4 adjacent outputs per thread) and solves.  Halo recompute: 256/240 columns x (rows + 14)/rows instead of the
 // 1.92x of the 48 x 32 tile kernel; moving down a column the upper two bilinear taps of a row are the lower two of
 // the previous row whenever the displacement is locally smooth, so they are reused from registers.
-constexpr int MS_SX = 240, MS_HALO = 8, MS_NT = 256, MS_RB = 4;
-constexpr int MS_SMEM = (15 * 5 * MS_NT + MS_RB * 5 * MS_NT) * 4;          // ring + row-batch buffer = 97,280 B
+constexpr int MS_HALO = 8, MS_RB = 4;
+// NT threads = NT - 16 output columns per strip.  256 threads x 2 CTAs / SM (97,280 B each) or 192 x 3 (72,960 B each: 18 warps / SM
+// instead of 16, strip efficiency 176/192 instead of 240/256)
+constexpr int ms_sx(int nt) { return nt - 2 * MS_HALO; }
+constexpr int ms_smem(int nt) { return (15 * 5 * nt + MS_RB * 5 * nt) * 4; }          // ring + row-batch buffer
 struct Tap2 { float4 a0, a1; float b0, b1; };                              // columns x1, x1 + 1 of one R1 row
 
 __device__ __forceinline__ Tap2 ld_tap2(const float4* __restrict__ ra, const float* __restrict__ rb, int q) {
   Tap2 t; t.a0 = ra[q]; t.a1 = ra[q + 1]; t.b0 = rb[q]; t.b1 = rb[q + 1]; return t;
 }
 
-template <bool kDoubleSums, bool kPrefetch>
-__global__ void __launch_bounds__(MS_NT, 2)
+template <bool kDoubleSums, bool kPrefetch, int MS_NT>
+__global__ void __launch_bounds__(MS_NT, MS_NT == 256 ? 2 : 3)
 k4_flow_iter_march(const float4* __restrict__ RA0, const float* __restrict__ RB0, const float4* __restrict__ RA1,
                    const float* __restrict__ RB1, const float* __restrict__ flow_in, int h, int w, int rows_per_seg,
                    float* __restrict__ flow_out) {
-  extern __shared__ __align__(16) float ms_smem[];
-  float* ring = ms_smem;                               // [15][5][MS_NT]
-  float* hb = ms_smem + 15 * 5 * MS_NT;                // [MS_RB][5][MS_NT] vertical sums of the current row batch
+  constexpr int MS_SX = MS_NT - 2 * MS_HALO;
+  extern __shared__ __align__(16) float ms_smem_buf[];
+  float* ring = ms_smem_buf;                               // [15][5][MS_NT]
+  float* hb = ms_smem_buf + 15 * 5 * MS_NT;                // [MS_RB][5][MS_NT] vertical sums of the current row batch
   const int tx = threadIdx.x;
   const int x0 = blockIdx.x * MS_SX;
   const int ya = blockIdx.y * rows_per_seg, yb = min(ya + rows_per_seg, h);
@@ -1046,9 +1050,9 @@ static int poly_rows_per_seg(int h, int w, int images, int sm_count) {
 // paying 14 warm-up rows (+ ~6 rows' worth of fixed cost).  The running sums make the last bits depend on where a
 // segment starts, so the split is a function of (h, w) alone (sized for a nominal batch of 22 pairs = one 10 s clip):
 // results stay bit-identical for any batch size / GPU count.
-static int march_rows_per_seg(int h, int w, int sm_count) {
+static int march_rows_per_seg(int h, int w, int sm_count, int MS_SX = 240, int per_sm = 2) {
   const int B = 22;
-  const long strips = cdiv(w, MS_SX), resident = 2L * sm_count;
+  const long strips = cdiv(w, MS_SX), resident = (long)per_sm * sm_count;
   double best = 1e30;
   int best_rs = (h + 3) & ~3;
   for (int nseg = 1; nseg <= cdiv(h, 8); ++nseg) {
@@ -1064,8 +1068,9 @@ static int march_rows_per_seg(int h, int w, int sm_count) {
 // Function attributes are per device: called by b200vqa_create for the context's device (not behind a process-wide flag).
 int flow_init_device_attrs() {
   VQA_CUDA(cudaFuncSetAttribute(k4_flow_iter, cudaFuncAttributeMaxDynamicSharedMemorySize, BX_SMEM));
-  VQA_CUDA(cudaFuncSetAttribute(k4_flow_iter_march<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MS_SMEM));
-  VQA_CUDA(cudaFuncSetAttribute(k4_flow_iter_march<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MS_SMEM));
+  VQA_CUDA(cudaFuncSetAttribute(k4_flow_iter_march<true, true, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, ms_smem(256)));
+  VQA_CUDA(cudaFuncSetAttribute(k4_flow_iter_march<false, true, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, ms_smem(256)));
+  VQA_CUDA(cudaFuncSetAttribute(k4_flow_iter_march<true, true, 192>, cudaFuncAttributeMaxDynamicSharedMemorySize, ms_smem(192)));
   VQA_CUDA(cudaFuncSetAttribute(k4_pyr_level<0, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
   VQA_CUDA(cudaFuncSetAttribute(k4_pyr_level<3, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
   VQA_CUDA(cudaFuncSetAttribute(k4_pyr_level<9, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
@@ -1142,8 +1147,9 @@ extern "C" int b200vqa_farneback(b200vqa_t* h, const uint8_t* gray0, const uint8
       VQA_LAUNCH_CHECK();
     }
     const dim3 gbox(cdiv(L.w, BX_TX), cdiv(L.h, BX_TY), B);
-    const int rows_per_seg = march_rows_per_seg(L.h, L.w, 148);      // fixed SM count: the split must not vary between devices
-    const dim3 gmarch(cdiv(L.w, MS_SX), cdiv(L.h, rows_per_seg), B);
+    const int nt = h->flow_impl == 3 ? 192 : 256;
+    const int rows_per_seg = march_rows_per_seg(L.h, L.w, 148, ms_sx(nt), nt == 256 ? 2 : 3);      // fixed SM count: the split must not vary between devices
+    const dim3 gmarch(cdiv(L.w, ms_sx(nt)), cdiv(L.h, rows_per_seg), B);
     float* fout = nullptr;
     for (int it = 0; it < 3; ++it) {
       fout = (last && it == 2) ? flow : (fin == flowA ? flowB : flowA);
@@ -1153,8 +1159,9 @@ extern "C" int b200vqa_farneback(b200vqa_t* h, const uint8_t* gray0, const uint8
         else { VQA_CUDA(cudaEventCreate(&ev.first)); VQA_CUDA(cudaEventCreate(&ev.second)); }
         VQA_CUDA(cudaEventRecord(ev.first, st));
       }
-      if (h->flow_impl == 0) k4_flow_iter_march<true, true><<<gmarch, MS_NT, MS_SMEM, st>>>(RA0, RB0, RA1, RB1, fin, L.h, L.w, rows_per_seg, fout);
-      else if (h->flow_impl == 1) k4_flow_iter_march<false, true><<<gmarch, MS_NT, MS_SMEM, st>>>(RA0, RB0, RA1, RB1, fin, L.h, L.w, rows_per_seg, fout);
+      if (h->flow_impl == 0) k4_flow_iter_march<true, true, 256><<<gmarch, 256, ms_smem(256), st>>>(RA0, RB0, RA1, RB1, fin, L.h, L.w, rows_per_seg, fout);
+      else if (h->flow_impl == 3) k4_flow_iter_march<true, true, 192><<<gmarch, 192, ms_smem(192), st>>>(RA0, RB0, RA1, RB1, fin, L.h, L.w, rows_per_seg, fout);
+      else if (h->flow_impl == 1) k4_flow_iter_march<false, true, 256><<<gmarch, 256, ms_smem(256), st>>>(RA0, RB0, RA1, RB1, fin, L.h, L.w, rows_per_seg, fout);
       else k4_flow_iter<<<gbox, 256, BX_SMEM, st>>>(RA0, RB0, RA1, RB1, fin, L.h, L.w, fout);
       if (h->profiling) {
         VQA_CUDA(cudaEventRecord(ev.second, st));

@@ -282,6 +282,52 @@ __device__ __forceinline__ void epi_row_direct_f16(const float* __restrict__ bia
   }
 }
 
+// fp32-output row epilogue without shared memory (proj / fc2 of the ViT: out = acc + bias + residual, fp32 residual stream).
+// Same idea as epi_row_direct_f16: a thread owns 32 consecutive columns of its accumulator row = 128 contiguous bytes, read
+// (residual) and written as 32-byte vectors, one full sector per lane and instruction; the 2 x 128 KB per 128 x 256 tile
+// that the staged transposition moves through the shared-memory port (27 % on top of the operand traffic of a K = 768
+// tile) disappear.  MEASURED (round 2, 264 images): ViT pass 13.84 ms with this path vs 13.64 ms with the staged one - the
+// linears are bound by L2 -> SM operand traffic (32 KB per K-block and SM against the ~42 B/clk/SM L2 cap), not by the
+// epilogue's shared-memory port share, and 128-byte-per-thread rows cost more LSU transactions.  Kept for A/B only.
+__device__ __forceinline__ void epi_row_direct_f32(const float* __restrict__ bias, const float* residual, float* out, int M, int ldo,
+                                                   int act, int block_n, uint32_t taddr, int m, int n0, int grp) {
+  for (int c0 = grp * 32; c0 < block_n; c0 += 32 * GEMM_EPI_GROUPS) {
+    uint32_t v[32];
+    tmem_ld32(taddr + c0, v);
+    float r[32];
+    const size_t o = (size_t)m * ldo + n0 + c0;
+    if (residual && m < M) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=f"(r[8 * i]), "=f"(r[8 * i + 1]), "=f"(r[8 * i + 2]), "=f"(r[8 * i + 3]), "=f"(r[8 * i + 4]), "=f"(r[8 * i + 5]),
+                       "=f"(r[8 * i + 6]), "=f"(r[8 * i + 7]) : "l"(residual + o + 8 * i) : "memory");
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) r[i] = 0.f;
+    }
+    tmem_ld_wait();
+    if (m < M) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float4 b0 = bias ? __ldg(reinterpret_cast<const float4*>(bias + n0 + c0) + 2 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 b1 = bias ? __ldg(reinterpret_cast<const float4*>(bias + n0 + c0) + 2 * i + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float bj8[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        float x[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float bj = bj8[j];
+          float t = __uint_as_float(v[8 * i + j]) + bj;
+          if (act == ACT_GELU) t = gelu_erf(t); else if (act == ACT_RELU) t = fmaxf(t, 0.f);
+          x[j] = t + r[8 * i + j];
+        }
+        asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(out + o + 8 * i), "f"(x[0]), "f"(x[1]), "f"(x[2]), "f"(x[3]),
+                     "f"(x[4]), "f"(x[5]), "f"(x[6]), "f"(x[7]) : "memory");
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------ the kernel
 #ifdef B200VQA_GEMM_KERNEL_TU      // defined by gemm_host.cu only (one definition per library)
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
@@ -695,6 +741,9 @@ gemm2cta_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
       if (p.dbg_skip_epilogue & 1) {
       } else if (!p.out_is_f32 && !p.residual && (p.ldo & 15) == 0 && !(p.dbg_skip_epilogue & 8)) {
         epi_row_direct_f16(p.bias, static_cast<__half*>(p.out), p.M, p.ldo, p.act, G2_BN, taddr,
+                           m2 * 256 + (int)rank * GEMM_BM + q * 32 + lane, nt * G2_BN, grp);
+      } else if (p.out_is_f32 && (p.ldo & 7) == 0 && (p.dbg_skip_epilogue & 16)) {      // A/B only (B200VQA_GEMM_NOEPI=16): measured slower, see below
+        epi_row_direct_f32(p.bias, p.residual, static_cast<float*>(p.out), p.M, p.ldo, p.act, G2_BN, taddr,
                            m2 * 256 + (int)rank * GEMM_BM + q * 32 + lane, nt * G2_BN, grp);
       } else {
         epi_row_fast(p.bias, p.residual, p.out, p.M, p.ldo, p.out_is_f32, p.act, G2_BN, taddr, epi_stage + (warp - 4) * (32 * EPI_LD),

@@ -153,6 +153,26 @@ class Engine:
             self._side = torch.cuda.Stream(self.device)
         return self._lane_list
 
+    #: clips of the same resolution are fused into one image-stage call of up to this many pair-pixels (0 = one call per clip)
+    GROUP_PIXELS = 0
+
+    def _units(self, clips):
+        """-> lists of clip indices; every list is one image-stage call on one lane."""
+        if not self.GROUP_PIXELS or not self.concurrent:
+            return [[i] for i in range(len(clips))]
+        units, open_units = [], {}
+        for i, c in enumerate(clips):
+            key = tuple(c.frames.shape[1:3])
+            px = max(1, c.nexts.shape[0]) * key[0] * key[1]
+            u = open_units.get(key)
+            if u is not None and u[1] + px <= self.GROUP_PIXELS:
+                u[0].append(i); u[1] += px
+            else:
+                u = [[i], px]
+                open_units[key] = u
+                units.append(u)
+        return [u[0] for u in units]
+
     def extract_blocks(self, clips: Sequence[Clip]):
         """-> dict of per-frame feature matrices stacked over clips + row offsets per clip."""
         ctx = self.ctx
@@ -164,26 +184,43 @@ class Engine:
         if not piped:
             for s, _ in lanes[:len(clips)]:
                 s.wait_stream(main)
-        for i, c in enumerate(clips):
-            s, lctx = lanes[i % len(lanes)]
+        for c in clips:
             if piped and c.ready is None:
                 # first use of this clip: everything queued on the current stream so far (its producer) is the dependency;
                 # later calls with the same (immutable) clip find the event complete and do not wait for earlier backbones
                 c.ready = torch.cuda.Event()
                 c.ready.record(main)
+        n = len(clips)
+        oris, mers, full_rn, full_vt = [None] * n, [None] * n, [None] * n, [None] * n
+        for u, unit in enumerate(self._units(clips)):
+            s, lctx = lanes[u % len(lanes)]
             with torch.cuda.stream(s):
-                if c.ready is not None:
-                    s.wait_event(c.ready)
-                tp = c.nexts.shape[0]
-                ori, mer = self.fragments(c.frames[:tp], c.nexts, ctx=lctx)
-                rn = ops.resize_pil(lctx, c.frames, ops.BILINEAR)
-                vt = ops.resize_pil(lctx, c.frames, ops.LANCZOS)
-            for t in (ori, mer, rn, vt, c.frames, c.nexts):
+                for i in unit:
+                    if clips[i].ready is not None:
+                        s.wait_event(clips[i].ready)
+                tps = [clips[i].nexts.shape[0] for i in unit]
+                tfs = [clips[i].frames.shape[0] for i in unit]
+                if len(unit) == 1:
+                    c = clips[unit[0]]
+                    fr_pairs, nx_pairs, fr_all = c.frames[:tps[0]], c.nexts, c.frames
+                else:       # clips of one resolution fused into one call: larger grids, fewer launches (results are batch-invariant)
+                    fr_pairs = torch.cat([clips[i].frames[:tp] for i, tp in zip(unit, tps)])
+                    nx_pairs = torch.cat([clips[i].nexts for i in unit])
+                    fr_all = torch.cat([clips[i].frames for i in unit])
+                ori, mer = self.fragments(fr_pairs, nx_pairs, ctx=lctx)
+                rn = ops.resize_pil(lctx, fr_all, ops.BILINEAR)
+                vt = ops.resize_pil(lctx, fr_all, ops.LANCZOS)
+            for t in [ori, mer, rn, vt] + [clips[i].frames for i in unit] + [clips[i].nexts for i in unit]:
                 t.record_stream(s)
                 t.record_stream(main)
-            oris.append(ori); mers.append(mer); full_rn.append(rn); full_vt.append(vt)
+            po = fo = 0
+            for i, tp, tf in zip(unit, tps, tfs):
+                oris[i], mers[i] = ori[po:po + tp], mer[po:po + tp]
+                full_rn[i], full_vt[i] = rn[fo:fo + tf], vt[fo:fo + tf]
+                po += tp; fo += tf
+        for c in clips:
             full_off.append(full_off[-1] + c.frames.shape[0])
-            pair_off.append(pair_off[-1] + tp)
+            pair_off.append(pair_off[-1] + c.nexts.shape[0])
         for s, _ in lanes[:len(clips)]:
             main.wait_stream(s)
         nf, npair = full_off[-1], pair_off[-1]

@@ -16,7 +16,7 @@ ap.add_argument("--height", type=int, default=1080)
 ap.add_argument("--width", type=int, default=1920)
 ap.add_argument("--pairs", type=int, default=22)
 ap.add_argument("--reps", type=int, default=5)
-ap.add_argument("--impls", default="2,1,0")
+ap.add_argument("--impls", default="2,1,0,3")
 ap.add_argument("--static", action="store_true", help="static scene + noise (near-zero flow: worst case for tap reuse)")
 args = ap.parse_args()
 

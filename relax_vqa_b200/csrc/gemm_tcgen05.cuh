@@ -671,6 +671,8 @@ gemm2cta_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
   }
   tcgen05_fence_before();
+  __syncthreads();         // orders the allocator's write of tmem_slot for this CTA's readers (the cluster barrier below does too, but
+                           // compute-sanitizer racecheck only models CTA barriers: round 1 reported 98 hazards on this read)
   cluster_sync_all();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;

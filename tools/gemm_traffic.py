@@ -1,9 +1,9 @@
 """ncu csv (dram__bytes_read.sum, dram__bytes_write.sum, gpu__time_duration.sum over the tcgen05 GEMM launches of one
-step) -> profiles/r1_gemm_traffic.json, the source of bench.py's roofline.traffic.
+step) -> profiles/gemm_traffic.json, the source of bench.py's roofline.traffic.
 
   ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none \
       --profile-from-start off -k regex:gemm --csv --log-file gpurun_out/gemm_traffic.csv python tools/profile_step.py --clips 4
-  python tools/gemm_traffic.py gpurun_out/gemm_traffic.csv profiles/r1_gemm_traffic.json"""
+  python tools/gemm_traffic.py gpurun_out/gemm_traffic.csv profiles/gemm_traffic.json"""
 import csv, json, sys
 
 rows = list(csv.reader(open(sys.argv[1])))

@@ -47,3 +47,78 @@ def test_ranks_compute_the_same_balanced_plan():
     assert plans[0] == plans[1]
     loads = [sum(costs[i] for i in r) for r in plans[0]]
     assert max(loads) / (sum(loads) / 8) < 1.02                             # finish times within 2 %
+
+
+# ---- the whole job on two ranks (gloo, CPU) with a stand-in engine: sharding, per-rank extraction, status gather, resume -------
+class _FakeEngine:
+    """Duck-typed Engine for the host logic: features are simple functions of the frames, so any rank computes the same
+    rows for the same video and the test can check who wrote what."""
+
+    def __init__(self):
+        import torch
+        self.device = torch.device("cpu")
+        self.calls = []
+
+    def extract_blocks(self, clips):
+        import torch
+        self.calls.append(len(clips))
+        fo, po = [0], [0]
+        for c in clips:
+            fo.append(fo[-1] + c.frames.shape[0]); po.append(po[-1] + c.nexts.shape[0])
+        fr = torch.cat([c.frames.float().mean(dim=(1, 2, 3)) for c in clips])        # clips of one batch may differ in resolution
+        nx = torch.cat([c.nexts.float().mean(dim=(1, 2, 3)) for c in clips])
+        wide = lambda t, w: t[:, None].expand(-1, w).contiguous()
+        return dict(full_resnet=wide(fr, 13120), full_vit=wide(fr, 2304), frag_stack=wide(nx, 13120), frag_pool=wide(nx, 2051),
+                    frag_vit_ori=wide(nx, 2304), frag_vit_mer=wide(nx, 2304), full_off=torch.tensor(fo), pair_off=torch.tensor(po))
+
+
+def _write_job(root, n=5):
+    import cv2
+    import pandas as pd
+    rng = np.random.default_rng(0)
+    sizes = [(32, 48), (16, 32), (32, 48), (48, 64), (16, 32)][:n]
+    for i, (h, w) in enumerate(sizes):
+        d = os.path.join(root, "frames", f"video_{i + 1}")
+        os.makedirs(d)
+        for k in range(2):
+            cv2.imwrite(os.path.join(d, f"v{i}_{k + 1}.png"), rng.integers(0, 256, (h, w, 3), dtype=np.uint8))
+            cv2.imwrite(os.path.join(d, f"v{i}_{k + 1}_next.png"), rng.integers(0, 256, (h, w, 3), dtype=np.uint8))
+    csv = os.path.join(root, "meta.csv")
+    pd.DataFrame(dict(vid=[f"v{i}" for i in range(n)], width=[s[1] for s in sizes], height=[s[0] for s in sizes], framerate=[29.97] * n,
+                      nb_frames=[30, 60, 30, 90, 60][:n])).to_csv(csv, index=False)
+    grey = os.path.join(root, "grey.csv")
+    pd.DataFrame({"index": [2], "vid": ["v2"]}).to_csv(grey, index=False)
+    return csv, grey
+
+
+def _job_worker(rank, world, port, root, ret):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    eng = _FakeEngine()
+    csv, grey = os.path.join(root, "meta.csv"), os.path.join(root, "grey.csv")
+    st = dd.run(csv, os.path.join(root, "frames"), os.path.join(root, "out"), "konvid_1k", engine=eng, batch_videos=2, greyscale_csv=grey)
+    ret[rank] = (st, sum(eng.calls))
+    dist.destroy_process_group()
+
+
+def test_job_on_two_ranks_gloo(tmp_path):
+    import torch.multiprocessing as mp
+    root = str(tmp_path)
+    _write_job(root)
+    ret = mp.Manager().dict()
+    mp.spawn(_job_worker, args=(2, 29700 + os.getpid() % 200, root, ret), nprocs=2, join=True)
+    st0, n0 = ret[0]
+    st1, n1 = ret[1]
+    assert st0 == st1 == [("v0", "done"), ("v1", "done"), ("v2", "greyscale"), ("v3", "done"), ("v4", "done")]    # gathered, metadata order
+    assert n0 + n1 == 4 and n0 > 0 and n1 > 0                                         # every video extracted once, by one rank
+    p = dd.output_paths(os.path.join(root, "out"), "konvid_1k", 3)
+    assert np.load(p["frag_resnet"]).shape == (2, 15171) and not os.path.exists(dd.output_paths(os.path.join(root, "out"), "konvid_1k", 2)["full_vit"])
+    # resume on one rank: everything is skipped, a truncated file is redone
+    with open(p["full_vit"], "r+b") as f:
+        f.truncate(100)
+    eng = _FakeEngine()
+    st = dd.run(os.path.join(root, "meta.csv"), os.path.join(root, "frames"), os.path.join(root, "out"), "konvid_1k", engine=eng,
+                greyscale_csv=os.path.join(root, "grey.csv"), rank=0, world=1)
+    assert [s for _, s in st] == ["skipped", "skipped", "greyscale", "done", "skipped"] and sum(eng.calls) == 1

@@ -199,7 +199,8 @@ int64_t b200vqa_launch_count(b200vqa_t* h);
  * every GEMM/conv, 2 = tcgen05 with the 1-CTA kernel everywhere (A/B measurements) */
 int b200vqa_set_gemm_impl(b200vqa_t* h, int impl);
 /* debug switch for the ViT attention (A/B measurements): 0 = tcgen05 / TMEM kernel (default: S = QK^T and O = PV on the 5th-gen
- * tensor cores, P kept in tensor memory), 1 = the warp-level mma.sync kernel of round 1 */
+ * tensor cores, P kept in tensor memory; two independent CTAs per SM), 1 = the warp-level mma.sync kernel of round 1,
+ * 2 = the tcgen05 kernel as one CTA per SM with two TMEM regions and the S product issued one tile ahead (measured slower) */
 int b200vqa_set_attn_impl(b200vqa_t* h, int impl);
 /* scheduling knob: persistent tcgen05 GEMM / conv grids of this context occupy at most `sms` SMs (even; 0 = all), leaving
  * the rest of the GPU to kernels running concurrently on other streams (the bandwidth stages of the next batch).  Results

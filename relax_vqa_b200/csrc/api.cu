@@ -87,7 +87,7 @@ extern "C" int b200vqa_set_gemm_impl(b200vqa_t* h, int impl) {
 }
 
 extern "C" int b200vqa_set_attn_impl(b200vqa_t* h, int impl) {
-  if (!h || impl < 0 || impl > 1) return B200VQA_EINVAL;
+  if (!h || impl < 0 || impl > 2) return B200VQA_EINVAL;
   h->attn_impl = impl;
   return B200VQA_OK;
 }

@@ -462,6 +462,209 @@ k10_attention_tc(const __grid_constant__ CUtensorMap map_q, const __grid_constan
   }
 }
 
+// ---- the same attention, software-pipelined inside one CTA per SM (A/B variant, attn_impl 2; MEASURED 96 us per 264-image
+// launch vs 91 us for the two-CTA version above - with two tiles in flight either way, throughput is two tiles per
+// tile-chain latency (~4.4 us: TMEM round trips of the two sweeps, barrier hops, P V, drain), and the single issuer thread
+// adds ordering stalls; not the default): all 512 TMEM columns as TWO score / output
+// regions and two shared-memory stages (one (image, head) item each).  The MMA issuer runs one query tile ahead: S of tile
+// n + 1 goes into the other region while the softmax of tile n is in progress, so a softmax group (8 warps per region) finds
+// its next scores ready when it has stored its outputs, and the exponentials of one region (XU-bound) overlap the P V, the
+// output drain and the barrier round trips of the other.  Tiles alternate regions; the two query tiles of an item swap
+// order on odd items, so both groups see the same mix of 128-row and 69-row tiles.
+constexpr int AT2_GROUP_WARPS = 8, AT2_GROUPS = 2;
+constexpr int AT2_THREADS = 64 + 32 * AT2_GROUP_WARPS * AT2_GROUPS;         // 576: warp 0 TMA, warp 1 TMEM alloc + MMA, 16 softmax warps
+constexpr uint32_t AT2_TMEM_COLS = 512, AT2_REGION = 256;
+constexpr int AT2_SMEM = 2 * ATC_STAGE_BYTES + AT2_GROUPS * 2 * 2 * 128 * 4 + 16 * 8 + 16 + 1024;
+
+__global__ void __launch_bounds__(AT2_THREADS, 1)
+k10_attention_tc2(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv, __half* __restrict__ out,
+                  int nimg, float scale) {
+  extern __shared__ __align__(1024) uint8_t atc_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(atc_raw) + 1023) & ~(uintptr_t)1023);
+  float* s_stat = reinterpret_cast<float*>(smem + 2 * ATC_STAGE_BYTES);       // [group][max | sum][half][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_stat + AT2_GROUPS * 2 * 2 * 128);
+  uint64_t* full_qk = bars; uint64_t* full_v = bars + 2; uint64_t* free_qk = bars + 4; uint64_t* free_v = bars + 6;      // per stage
+  uint64_t* s_full = bars + 8; uint64_t* p_full = bars + 10; uint64_t* o_full = bars + 12; uint64_t* s_free = bars + 14;  // per region
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_q) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_kv) : "memory");
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&full_qk[i], 1); mbar_init(&full_v[i], 1); mbar_init(&free_qk[i], 1); mbar_init(&free_v[i], 1);
+      mbar_init(&s_full[i], 1); mbar_init(&p_full[i], AT2_GROUP_WARPS); mbar_init(&o_full[i], 1); mbar_init(&s_free[i], AT2_GROUP_WARPS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(AT2_TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int items = nimg * VH;
+  const int my_items = items > (int)blockIdx.x ? (items - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  const int ntiles = 2 * my_items;
+  // tile n of this CTA: item it = n / 2 (global item blockIdx.x + it * gridDim.x), query tile t, region n & 1, stage it & 1
+  auto tile_t = [](int n) { return ((n >> 1) & 1) ? 1 - (n & 1) : (n & 1); };
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    if (lane == 0) {
+      for (int it = 0; it < my_items; ++it) {
+        const int item = blockIdx.x + it * gridDim.x;
+        const int b = item / VH, hh = item - b * VH;
+        const int st = it & 1;
+        const uint32_t par = (uint32_t)((it >> 1) & 1);
+        uint8_t* base = smem + (size_t)st * ATC_STAGE_BYTES;
+        mbar_wait(&free_qk[st], par ^ 1u);
+        mbar_expect_tx(&full_qk[st], 2 * ATC_Q_BYTES + ATC_KV_BYTES);
+        tma_load_2d(&map_q, &full_qk[st], base, hh * VHD, b * VT);
+        tma_load_2d(&map_q, &full_qk[st], base + ATC_Q_BYTES, hh * VHD, b * VT + 128);
+        tma_load_2d(&map_kv, &full_qk[st], base + 2 * ATC_Q_BYTES, VD + hh * VHD, b * VT);
+        mbar_wait(&free_v[st], par ^ 1u);
+        mbar_expect_tx(&full_v[st], ATC_KV_BYTES);
+        tma_load_2d(&map_kv, &full_v[st], base + 2 * ATC_Q_BYTES + ATC_KV_BYTES, 2 * VD + hh * VHD, b * VT);
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ==================================
+    if (lane == 0 && ntiles > 0) {
+      const uint32_t idesc_s = make_idesc(ATC_KV_ROWS);                      // A, B K-major
+      const uint32_t idesc_o = make_idesc(VHD) | (1u << 16);                  // B (V) MN-major
+      auto issue_s = [&](int n) {
+        const int it = n >> 1, st = it & 1, r = n & 1, t = tile_t(n);
+        if ((n & 1) == 0) { mbar_wait(&full_qk[st], (uint32_t)((it >> 1) & 1)); }
+        mbar_wait(&s_free[r], (uint32_t)((n >> 1) & 1) ^ 1u);                 // O of the region's previous tile has been read out
+        tcgen05_fence_after();
+        const uint32_t sb = smem_u32(smem + (size_t)st * ATC_STAGE_BYTES);
+        const uint64_t dQ = make_smem_desc(sb + (uint32_t)t * ATC_Q_BYTES), dK = make_smem_desc(sb + 2 * ATC_Q_BYTES);
+#pragma unroll
+        for (int k = 0; k < VHD / 16; ++k)
+          tcgen05_mma_f16(tmem_base + (uint32_t)r * AT2_REGION, dQ + (uint64_t)(2 * k), dK + (uint64_t)(2 * k), idesc_s, k != 0);
+        tcgen05_commit(&s_full[r]);
+        if (n & 1) tcgen05_commit(&free_qk[st]);                              // both S products of the item are issued
+      };
+      issue_s(0);
+      for (int n = 0; n < ntiles; ++n) {
+        if (n + 1 < ntiles) issue_s(n + 1);                                   // one tile ahead, into the other region
+        const int it = n >> 1, st = it & 1, r = n & 1;
+        mbar_wait(&p_full[r], (uint32_t)((n >> 1) & 1));
+        if ((n & 1) == 0) mbar_wait(&full_v[st], (uint32_t)((it >> 1) & 1));
+        tcgen05_fence_after();
+        const uint64_t dV = make_smem_desc(smem_u32(smem + (size_t)st * ATC_STAGE_BYTES) + 2 * ATC_Q_BYTES + ATC_KV_BYTES);
+        const uint32_t rb = tmem_base + (uint32_t)r * AT2_REGION;
+#pragma unroll
+        for (int k = 0; k < ATC_KV_ROWS / 16; ++k) {
+          const uint32_t pcol = k < ATC_SPLIT / 16 ? (uint32_t)(8 * k) : ATC_PB_COL + (uint32_t)(8 * (k - ATC_SPLIT / 16));
+          tcgen05_mma_f16_ts(rb + ATC_O_COL, rb + pcol, dV + (uint64_t)(128 * k), idesc_o, k != 0);
+        }
+        tcgen05_commit(&o_full[r]);
+        if (n & 1) tcgen05_commit(&free_v[st]);
+      }
+    }
+  } else {
+    // ================================ softmax / epilogue: group g owns region g ======================
+    const int sw = warp - 2;                                                  // 0..15
+    const int g = sw >> 3, half = (sw >> 2) & 1, q = warp & 3;                // region, key half (A / B), TMEM lane quadrant
+    const int rl = q * 32 + lane;
+    const uint32_t taddr = tmem_base + (uint32_t)g * AT2_REGION + ((uint32_t)(q * 32) << 16);
+    const int col0 = half ? ATC_SPLIT : 0, nchunk = half ? (ATC_KV_ROWS - ATC_SPLIT) / 16 : ATC_SPLIT / 16;
+    const uint32_t pcol0 = half ? ATC_PB_COL : 0u;
+    float* s_max = s_stat + g * 512; float* s_sum = s_max + 256;
+    const float sl2 = scale * 1.4426950408889634f;
+    for (int n = g; n < ntiles; n += 2) {
+      const int it = n >> 1, t = tile_t(n);
+      const int item = blockIdx.x + it * gridDim.x;
+      const int b = item / VH, hh = item - b * VH;
+      const uint32_t par = (uint32_t)((n >> 1) & 1);
+      const int row = t * 128 + rl;
+      const bool warp_valid = t * 128 + q * 32 < VT;                          // warp-uniform
+      mbar_wait(&s_full[g], par);
+      tcgen05_fence_after();
+      float m = -INFINITY;
+      if (warp_valid) {
+        uint32_t v[2][16];
+        tmem_ld16(taddr + col0, v[0]);
+#pragma unroll
+        for (int c = 0; c < 7; ++c) {
+          if (c < nchunk) {
+            tmem_ld_wait();
+            if (c + 1 < nchunk) tmem_ld16(taddr + col0 + 16 * (c + 1), v[(c + 1) & 1]);
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (col0 + 16 * c + j < VT) m = fmaxf(m, __uint_as_float(v[c & 1][j]));
+          }
+        }
+        s_max[half * 128 + rl] = m;
+      }
+      named_bar_sync(1 + 2 * g, 32 * AT2_GROUP_WARPS);
+      float inv_l = 0.f;
+      if (warp_valid) {
+        m = fmaxf(m, s_max[(half ^ 1) * 128 + rl]);
+        const float mk = m * sl2;
+        float l = 0.f;
+        uint32_t v[2][16];
+        tmem_ld16(taddr + col0, v[0]);
+#pragma unroll
+        for (int c = 0; c < 7; ++c) {
+          if (c < nchunk) {
+            tmem_ld_wait();
+            if (c + 1 < nchunk) tmem_ld16(taddr + col0 + 16 * (c + 1), v[(c + 1) & 1]);
+            uint32_t pk[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int k0 = col0 + 16 * c + 2 * j;
+              const float p0 = k0 < VT ? ex2_approx(fmaf(__uint_as_float(v[c & 1][2 * j]), sl2, -mk)) : 0.f;
+              const float p1 = k0 + 1 < VT ? ex2_approx(fmaf(__uint_as_float(v[c & 1][2 * j + 1]), sl2, -mk)) : 0.f;
+              l += p0 + p1;
+              pk[j] = pack_h2(p0, p1);
+            }
+            tmem_st8(taddr + pcol0 + 8 * c, pk);
+          }
+        }
+        tmem_st_wait();
+        s_sum[half * 128 + rl] = l;
+      }
+      tcgen05_fence_before();
+      named_bar_sync(2 + 2 * g, 32 * AT2_GROUP_WARPS);
+      if (lane == 0) mbar_arrive(&p_full[g]);
+      if (warp_valid) inv_l = 1.0f / (s_sum[rl] + s_sum[128 + rl]);
+      mbar_wait(&o_full[g], par);
+      tcgen05_fence_after();
+      if (warp_valid) {
+        uint32_t o[32];
+        tmem_ld32(taddr + ATC_O_COL + 32 * half, o);
+        tmem_ld_wait();
+        if (row < VT) {
+          __half* op = out + ((size_t)b * VT + row) * VD + hh * VHD + 32 * half;
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            uint32_t h8[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              h8[j] = pack_h2(__uint_as_float(o[16 * i + 2 * j]) * inv_l, __uint_as_float(o[16 * i + 2 * j + 1]) * inv_l);
+            asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(op + 16 * i), "r"(h8[0]), "r"(h8[1]), "r"(h8[2]),
+                         "r"(h8[3]), "r"(h8[4]), "r"(h8[5]), "r"(h8[6]), "r"(h8[7]) : "memory");
+          }
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_free[g]);
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(AT2_TMEM_COLS) : "memory");
+  }
+}
+
 // SIMT check version of the attention (one thread per (query, head-dim) output)
 __global__ void ref_attention(const __half* __restrict__ qkv, __half* __restrict__ out, float scale) {
   const int hh = blockIdx.x, b = blockIdx.y, q = blockIdx.z;
@@ -554,6 +757,7 @@ k11_final_norm_tokens(const float* __restrict__ x, const float* __restrict__ w, 
 int vit_init_device_attrs() {
   VQA_CUDA(cudaFuncSetAttribute(k10_attention, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
   VQA_CUDA(cudaFuncSetAttribute(k10_attention_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC_SMEM));
+  VQA_CUDA(cudaFuncSetAttribute(k10_attention_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, AT2_SMEM));
   return B200VQA_OK;
 }
 
@@ -689,8 +893,12 @@ static int vit_forward(b200vqa_t* h, const uint8_t* img, int B, int is_bgr, floa
         uint32_t boxq[2] = {VHD, 128}, boxkv[2] = {VHD, ATC_KV_ROWS};
         if ((rc = make_tmap_f16(&mq, big, 2, dims, strides, boxq, nullptr))) return rc;
         if ((rc = make_tmap_f16(&mkv, big, 2, dims, strides, boxkv, nullptr))) return rc;
-        const int items = n * VH, grid = items < 2 * h->sm_count ? items : 2 * h->sm_count;
-        k10_attention_tc<<<grid, ATC_THREADS, ATC_SMEM, st>>>(mq, mkv, att, n, 0.125f);
+        const int items = n * VH;
+        if (h->attn_impl == 2) {          // A/B: one CTA per SM, two TMEM regions, S issued one tile ahead
+          k10_attention_tc2<<<items < h->sm_count ? items : h->sm_count, AT2_THREADS, AT2_SMEM, st>>>(mq, mkv, att, n, 0.125f);
+        } else {                          // default: two independent CTAs per SM
+          k10_attention_tc<<<items < 2 * h->sm_count ? items : 2 * h->sm_count, ATC_THREADS, ATC_SMEM, st>>>(mq, mkv, att, n, 0.125f);
+        }
       }
       VQA_LAUNCH_CHECK();
       if ((rc = run_linear(h, bk.proj, att, m, x, 1, ACT_NONE, x, st))) return rc;

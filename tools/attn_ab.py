@@ -18,7 +18,7 @@ ctx = ops.Context(0)
 ops.load_vitb16(ctx, weights.seeded_vitb16_state_dict())
 img = torch.randint(0, 256, (a.images, 224, 224, 3), dtype=torch.uint8, device="cuda")
 res = {}
-for impl in (1, 0):
+for impl in (1, 2, 0):
     ctx.set_attn_impl(impl)
     for _ in range(3):
         out = ops.vitb16_features(ctx, img)
@@ -35,12 +35,12 @@ small = img[:6].contiguous()
 ctx.set_gemm_impl(1)
 chk = ops.vitb16_features(ctx, small)
 ctx.set_gemm_impl(0)
-for impl in (1, 0):
+for impl in (1, 2, 0):
     ctx.set_attn_impl(impl)
     got = ops.vitb16_features(ctx, small)
     err = (got - chk).abs().max().item() / chk.pow(2).mean().sqrt().item()
     print(f"attn_impl={impl} vs SIMT check: max|d|/rms = {err:.2e}")
 d = (res[0][1] - res[1][1]).abs().max().item() / res[1][1].pow(2).mean().sqrt().item()
 print(f"tcgen05 vs mma.sync attention: max|d|/rms = {d:.2e}; saving per ViT pass {res[1][0] - res[0][0]:.3f} ms "
-      f"= {(res[1][0] - res[0][0]) / 12 * 1e3:.1f} us per attention launch")
+      f"= {(res[1][0] - res[0][0]) / 12 * 1e3:.1f} us per attention launch (2-CTA/SM version: {(res[1][0] - res[2][0]) / 12 * 1e3:.1f} us)")
 ctx.close()

@@ -1,6 +1,7 @@
 // Context management and error reporting for libb200vqa.
 #include <string.h>
 #include <string>
+#include <stdlib.h>
 #include "context.h"
 
 namespace b200vqa {
@@ -60,6 +61,7 @@ extern "C" int b200vqa_create(int device, b200vqa_t** out) {
   b200vqa_ctx* h = new b200vqa_ctx();
   h->device = device;
   h->sm_count = prop.multiProcessorCount;
+  if (const char* e = getenv("B200VQA_FLOW_IMPL")) h->flow_impl = atoi(e);      // A/B switch for tools / bench
   *out = h;
   return B200VQA_OK;
 }
@@ -99,7 +101,7 @@ extern "C" int b200vqa_set_gemm_sms(b200vqa_t* h, int sms) {
 }
 
 extern "C" int b200vqa_set_flow_impl(b200vqa_t* h, int impl) {
-  if (!h || impl < 0 || impl > 3) return B200VQA_EINVAL;
+  if (!h || impl < 0 || impl > 5) return B200VQA_EINVAL;
   h->flow_impl = impl;
   return B200VQA_OK;
 }

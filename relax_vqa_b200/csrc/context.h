@@ -35,7 +35,8 @@ struct b200vqa_ctx {
   int gemm_sms = 0;                        // > 0: persistent tcgen05 grids use this many SMs (b200vqa_set_gemm_sms)
   int gemm_impl = 0;                       // 0 tcgen05, 1 SIMT check kernels
   int attn_impl = 0;                       // 0 tcgen05 / TMEM attention, 1 warp-level mma.sync attention (A/B)
-  int flow_impl = 0;                       // 0 streaming strip kernels (f64 running sums), 1 same with Kahan fp32 sums, 2 tile kernels
+  int flow_impl = 0;                       // 0 streaming strip kernels (f64 running sums), 1 same with Kahan fp32 sums, 2 tile kernels,
+                                           // 3 192-thread strips, 4 software-pipelined variant (march3), 5 same with the first version's solve
   int64_t launches = 0;
   int profiling = 0;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;          // class 0: tcgen05 GEMM / conv launches

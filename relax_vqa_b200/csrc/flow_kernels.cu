@@ -779,6 +779,236 @@ k4_flow_iter_march(const float4* __restrict__ RA0, const float* __restrict__ RB0
   }
 }
 
+// ---- (d+e), streaming form, second version (A/B variant, NOT the default: same speed; profiles/r2_flow_experiments.md).
+// k4_flow_iter_march3 keeps the dataflow of k4_flow_iter_march and cuts the instruction count per pixel from ~340 to ~290
+// (an intermediate version without the software pipeline reached ~250):
+//  * every global address is ONE 64-bit multiply-add from a 32-bit pixel index against a per-image base pointer held in
+//    registers (the first version spends 4 integer instructions per address on 11 addresses per pixel);
+//  * the per-thread L2 prefetches (4 addresses per pixel, each with its own floor / clamp / address chain) became one
+//    prefetch instruction per row issued by 14 lanes of the warp (details at the kernel);
+//  * the bilinear taps and half of UpdateMatrices run on the packed fp32x2 pipe (the float4 coefficient layout puts
+//    (y, x) and (yy, xx) in aligned register pairs);
+//  * the row-batch buffer holds the five vertical sums as three float2 planes, so the horizontal 15-sums are packed
+//    adds (60 instead of 100 per 4 outputs) on the same 128-bit shared-memory windows, conflict-free with a row pitch
+//    of 16 B mod 128 B and two rows per quarter-warp;
+//  * the 2x2 solve keeps OpenCV's fp64 determinants (products of fp32 values are exact in fp64) with the 1/225^2 scale
+//    folded into the regulariser, and divides in fp32 (relative 2e-7: < 1e-5 px) instead of a 12-instruction fp64
+//    reciprocal.  kExactSolve keeps the first version's solve: with it the two kernels agree bit for bit
+//    (tools/flow_ab.py), which is how this one was checked.
+// Measured: the instruction diet alone changed nothing (issue slots 58 % -> 41 % busy, same 750 us per level-0 launch):
+// the kernel is bound by dependent-instruction latency at 4 warps per scheduler (ring + registers cap the SM at 16 warps).
+constexpr int M2_NT = 256, M2_SX = M2_NT - 2 * MS_HALO, M2_P2 = M2_NT + 2;              // hb row pitch: 258 float2 = 2064 B
+constexpr int m2_smem() { return 15 * 5 * M2_NT * 4 + 3 * MS_RB * M2_P2 * 8; }         // ring + row-batch buffer = 101,568 B
+
+__device__ __forceinline__ float2 lo2(const float4& v) { return make_float2(v.x, v.y); }
+__device__ __forceinline__ float2 hi2(const float4& v) { return make_float2(v.z, v.w); }
+// a00 t00 + a01 t01 + a10 t10 + a11 t11, in the association the first version compiled to
+__device__ __forceinline__ float2 bil2(float2 w00, float2 w01, float2 w10, float2 w11, float2 t00, float2 t01, float2 t10, float2 t11) {
+  float2 r = __fmul2_rn(w01, t01);
+  r = __ffma2_rn(w00, t00, r);
+  r = __ffma2_rn(w10, t10, r);
+  return __ffma2_rn(w11, t11, r);
+}
+
+// Software pipeline: the loads of row k + 1 (R0, flow-displaced R1 taps) are issued BEFORE the arithmetic of row k, so a
+// row's worth of instructions (x 4 warps per scheduler) covers their latency.  Two register sets (even / odd rows) hold
+// the in-flight row; the lower taps of the row just finished are copied to `T` (the upper taps of the next row when the
+// displacement is locally smooth) before their set is reloaded.  Flow vectors run four rows ahead; the row prefetcher
+// (one instruction per row, lanes 0-13) requests the R0 / R1 lines of row k + 3 (R1 rows and columns shifted by the
+// lane's own displacement one row earlier) and the flow lines of row k + 8 into L2.
+// Same arithmetic in the same order as k4_flow_iter_march: kExactSolve gives bit-identical flow.
+struct M3Row { float4 c0; float c0xy; Tap2 bot; float2 d; float fx, fy; int q, yv; bool in; };
+
+template <bool kExactSolve>
+__global__ void __launch_bounds__(M2_NT, 2)
+k4_flow_iter_march3(const float4* __restrict__ RA0, const float* __restrict__ RB0, const float4* __restrict__ RA1,
+                    const float* __restrict__ RB1, const float* __restrict__ flow_in, int h, int w, int rows_per_seg,
+                    float* __restrict__ flow_out) {
+  extern __shared__ __align__(16) float ms_smem_buf[];
+  float* ring = ms_smem_buf;                                                       // [15][5][M2_NT]
+  float2* hb = reinterpret_cast<float2*>(ms_smem_buf + 15 * 5 * M2_NT);            // [3][MS_RB][M2_P2]: (m0,m1) (m2,m3) (m4,-)
+  const int tx = threadIdx.x;
+  const int x0 = blockIdx.x * M2_SX;
+  const int ya = blockIdx.y * rows_per_seg, yb = min(ya + rows_per_seg, h);
+  const size_t zo = (size_t)blockIdx.z * h * w;
+  const float2* fin = reinterpret_cast<const float2*>(flow_in) + zo;
+  const float4* ra0 = RA0 + zo; const float* rb0 = RB0 + zo;
+  const float4* ra1 = RA1 + zo; const float* rb1 = RB1 + zo;
+  asm volatile("" : "+l"(fin), "+l"(ra0), "+l"(rb0), "+l"(ra1), "+l"(rb1));        // opaque: addresses = base + 32-bit index
+  __builtin_assume(__isGlobal(fin)); __builtin_assume(__isGlobal(ra0)); __builtin_assume(__isGlobal(rb0));
+  __builtin_assume(__isGlobal(ra1)); __builtin_assume(__isGlobal(rb1));
+  const int x = min(max(x0 - MS_HALO + tx, 0), w - 1);                             // replicate border: M at the clamped pixel
+  const bool xedge = (unsigned)(x - 5) >= (unsigned)(w - 10);
+  const float bwx = border_w(x, w), xf = (float)x;
+  const int nk = 14 + ((yb - ya + MS_RB - 1) & ~(MS_RB - 1));                      // rows of M this block walks (even)
+  // row prefetcher of this lane: base pointer (at the line's first pixel), row pitch in bytes, row / column follow the flow?
+  const int lane = tx & 31;
+  const char* pf_base; int pf_pitch, pf_follow, pf_esz, pf_ahead, pf_px;
+  {
+    const int xw = x0 - MS_HALO + (tx & ~31);
+    pf_px = lane < 8 ? xw + 8 * (lane & 3) : (lane < 12 ? xw + 31 * (lane & 1) : xw + 16 * (lane & 1));
+    if (lane < 4) { pf_base = reinterpret_cast<const char*>(ra0); pf_esz = 16; pf_follow = 0; pf_ahead = 3; }
+    else if (lane < 8) { pf_base = reinterpret_cast<const char*>(ra1); pf_esz = 16; pf_follow = 1; pf_ahead = 3; }
+    else if (lane < 10) { pf_base = reinterpret_cast<const char*>(rb0); pf_esz = 4; pf_follow = 0; pf_ahead = 3; }
+    else if (lane < 12) { pf_base = reinterpret_cast<const char*>(rb1); pf_esz = 4; pf_follow = 1; pf_ahead = 3; }
+    else { pf_base = reinterpret_cast<const char*>(fin); pf_esz = 8; pf_follow = 0; pf_ahead = 8; }
+    pf_pitch = pf_esz * w;
+  }
+  const bool pf_on = lane < 14;
+  double vd[5];
+#pragma unroll
+  for (int c = 0; c < 5; ++c) vd[c] = 0.0;
+  int slot = 0;
+  const float2 neg1 = make_float2(-1.f, -1.f), one2 = make_float2(1.f, 1.f), half2 = make_float2(0.5f, 0.5f);
+  auto row_y = [&](int kk) { return min(max(ya - 7 + kk, 0), h - 1); };
+  // start the loads of march row kk (flow vector d): first-image coefficients at the pixel, lower taps of the second image
+  auto issue = [&](M3Row& R, int kk, float2 d) {
+    R.yv = row_y(kk);
+    const int o = R.yv * w + x;
+    R.d = d; R.c0 = ra0[o]; R.c0xy = rb0[o];
+    const float gxf = xf + d.x, gyf = (float)R.yv + d.y;
+    const int x1 = __float2int_rd(gxf), y1 = __float2int_rd(gyf);
+    R.fx = gxf - (float)x1; R.fy = gyf - (float)y1;
+    R.in = (unsigned)x1 < (unsigned)(w - 1) && (unsigned)y1 < (unsigned)(h - 1);
+    R.q = R.in ? y1 * w + x1 : 0;                                                  // outside: any valid address, result unused
+    R.bot = ld_tap2(ra1, rb1, R.q + w);
+  };
+  // UpdateMatrices at the row's pixel + vertical running sums + row-batch buffer
+  auto compute = [&](const M3Row& R, const Tap2& top, int kk) {
+    const float dx = R.d.x, dy = R.d.y;
+    const float2 fx2 = make_float2(R.fx, R.fx), fy2 = make_float2(R.fy, R.fy);
+    const float2 ox2 = __ffma2_rn(fx2, neg1, one2), oy2 = __ffma2_rn(fy2, neg1, one2);
+    const float2 w00 = __fmul2_rn(ox2, oy2), w01 = __fmul2_rn(fx2, oy2), w10 = __fmul2_rn(ox2, fy2), w11 = __fmul2_rn(fx2, fy2);
+    float2 r23 = bil2(w00, w01, w10, w11, lo2(top.a0), lo2(top.a1), lo2(R.bot.a0), lo2(R.bot.a1));
+    float2 r45 = bil2(w00, w01, w10, w11, hi2(top.a0), hi2(top.a1), hi2(R.bot.a0), hi2(R.bot.a1));
+    float r6 = w01.x * top.b1;
+    r6 = fmaf(w00.x, top.b0, r6); r6 = fmaf(w10.x, R.bot.b0, r6); r6 = fmaf(w11.x, R.bot.b1, r6);
+    // outside the image: r2 = r3 = 0 and the second image's quadratic terms are replaced by the first image's
+    r23.x = R.in ? r23.x : 0.f; r23.y = R.in ? r23.y : 0.f;
+    r45.x = R.in ? r45.x : R.c0.z; r45.y = R.in ? r45.y : R.c0.w;
+    r6 = R.in ? r6 : R.c0xy;
+    r45 = __fmul2_rn(__fadd2_rn(hi2(R.c0), r45), half2);
+    r6 = (R.c0xy + r6) * 0.25f;
+    r23 = __ffma2_rn(r23, neg1, lo2(R.c0));
+    float r2 = fmaf(r23.x, 0.5f, fmaf(r45.x, dy, r6 * dx));
+    float r3 = fmaf(r23.y, 0.5f, fmaf(r45.y, dx, r6 * dy));
+    float r4 = r45.x, r5 = r45.y;
+    if (xedge || (unsigned)(R.yv - 5) >= (unsigned)(h - 10)) {
+      const float s = border_w(R.yv, h) * bwx;
+      r2 *= s; r3 *= s; r4 *= s; r5 *= s; r6 *= s;
+    }
+    float m[5];
+    const float r66 = r6 * r6;
+    m[0] = fmaf(r4, r4, r66);
+    m[1] = (r4 + r5) * r6;
+    m[2] = fmaf(r5, r5, r66);
+    m[3] = fmaf(r2, r4, r3 * r6);
+    m[4] = fmaf(r3, r5, r2 * r6);
+    float* rp = ring + slot * (5 * M2_NT) + tx;
+    float vs[5];
+#pragma unroll
+    for (int c = 0; c < 5; ++c) {
+      double inc = (double)m[c];
+      if (kk >= 15) inc -= (double)rp[c * M2_NT];                                  // exact in f64
+      rp[c * M2_NT] = m[c];
+      vd[c] += inc;
+      vs[c] = (float)vd[c];
+    }
+    slot = slot == 14 ? 0 : slot + 1;
+    if (kk >= 14) {
+      float2* hp = hb + ((kk - 14) & (MS_RB - 1)) * M2_P2 + tx;
+      hp[0] = make_float2(vs[0], vs[1]);
+      hp[MS_RB * M2_P2] = make_float2(vs[2], vs[3]);
+      hp[2 * MS_RB * M2_P2] = make_float2(vs[4], 0.f);
+    }
+  };
+  // flow vectors of march rows kk + 1 .. kk + 3 (f2, f3, f4); row kk's is in its register set
+  M3Row X, Y;
+  Tap2 T; T.a0 = T.a1 = make_float4(0.f, 0.f, 0.f, 0.f); T.b0 = T.b1 = 0.f;
+  int tq = -1;                                                                     // pixel index of the row held in T
+  float2 f2 = fin[row_y(1) * w + x], f3 = fin[row_y(2) * w + x], f4 = fin[row_y(3) * w + x];
+  issue(X, 0, fin[row_y(0) * w + x]);
+  // one pipeline step: prefetch for row kk + 3, flow of row kk + 4, loads of row kk + 1 into N, arithmetic of row kk from C
+  const unsigned ones = h > 0 ? 0xffffffffu : 0u;                                  // all-ones the compiler cannot fold
+  auto step = [&](M3Row& C, M3Row& N, int kk) {
+    // Row kk's loads must have landed before row kk + 1's are issued: ptxas tracks every global load of this kernel on
+    // ONE scoreboard counter, so a consumer of row kk issued after row kk + 1's loads would wait for those as well
+    // (that is what march3 did without this line: tools/sbdecode.py).  A warp barrier whose mask depends on a loaded
+    // value waits for the counter here, and keeps ptxas from hoisting the next loads above it.
+    __syncwarp(__float_as_uint(C.c0xy) | ones);
+    {
+      const int prow = min(max(row_y(kk + pf_ahead) + pf_follow * (__float2int_rd(f3.y) + 1), 0), h - 1);
+      const int pcol = min(max(pf_px + pf_follow * __float2int_rd(f3.x), 0), w - 1);
+      if (pf_on) asm volatile("prefetch.global.L2 [%0];" ::"l"(pf_base + (long long)prow * pf_pitch + pcol * pf_esz));
+    }
+    const float2 fnew = fin[row_y(kk + 4) * w + x];
+    issue(N, kk + 1, f2);
+    if (C.q != tq) T = ld_tap2(ra1, rb1, C.q);                                     // upper taps = the previous row's lower taps, usually
+    compute(C, T, kk);
+    T = C.bot; tq = C.q + w;
+    f2 = f3; f3 = f4; f4 = fnew;
+  };
+  for (int k = 0; k < nk; k += 2) {
+    step(X, Y, k);
+    step(Y, X, k + 1);
+    if (k >= 16 && (k & 3) == 0) {
+      // rows ya + k - 16 .. ya + k - 13 are complete: horizontal 15-sums (slots o+1 .. o+15 for output o) + solve.
+      // threads 2 qd + (j & 1) + 120 (j >> 1): a quarter-warp reads 4 windows x 2 rows = 8 distinct 16-byte bank groups
+      __syncthreads();
+      if (tx < MS_RB * (M2_SX / 4)) {
+        const int hf = tx >= 2 * (M2_SX / 4) ? 1 : 0, tt = tx - hf * 2 * (M2_SX / 4);
+        const int j = 2 * hf + (tt & 1), qd = tt >> 1;
+        const int gy = ya + k - 16 + j, gx0 = x0 + 4 * qd;
+        float2 g[3][4];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+          const float4* p = reinterpret_cast<const float4*>(hb + (a * MS_RB + j) * M2_P2 + 4 * qd);
+          float2 wv[20];
+#pragma unroll
+          for (int i = 0; i < 10; ++i) { const float4 v = p[i]; wv[2 * i] = make_float2(v.x, v.y); wv[2 * i + 1] = make_float2(v.z, v.w); }
+          float2 s = wv[1];
+#pragma unroll
+          for (int i = 2; i <= 15; ++i) s = __fadd2_rn(s, wv[i]);
+          g[a][0] = s;
+#pragma unroll
+          for (int o = 1; o < 4; ++o) { s = __fadd2_rn(s, __ffma2_rn(wv[o], neg1, wv[o + 15])); g[a][o] = s; }
+        }
+        if (gy < yb && gx0 < w) {
+          float2 f[4];
+#pragma unroll
+          for (int o = 0; o < 4; ++o) {
+            if (kExactSolve) {
+              const double sc = 1.0 / 225.0;
+              const double g11 = g[0][o].x * sc, g12 = g[0][o].y * sc, g22 = g[1][o].x * sc, h1 = g[1][o].y * sc, h2 = g[2][o].x * sc;
+              const double idet = 1.0 / (g11 * g22 - g12 * g12 + 1e-3);
+              f[o].x = (float)((g11 * h2 - g12 * h1) * idet);
+              f[o].y = (float)((g22 * h1 - g12 * h2) * idet);
+            } else {
+              // flow = (G11 H2 - G12 H1, G22 H1 - G12 H2) / (G11 G22 - G12^2 + 1e-3 * 225^2) on the un-scaled sums
+              const double g11 = g[0][o].x, g12 = g[0][o].y, g22 = g[1][o].x, h1 = g[1][o].y, h2 = g[2][o].x;
+              const float det = (float)fma(g11, g22, fma(-g12, g12, 1e-3 * 225.0 * 225.0));
+              const float n1 = (float)fma(g11, h2, -(g12 * h1)), n2 = (float)fma(g22, h1, -(g12 * h2));
+              float idet;
+              asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(idet) : "f"(det));            // det >= 50.6: one MUFU, 1 ulp
+              f[o].x = n1 * idet; f[o].y = n2 * idet;
+            }
+          }
+          const size_t oi = zo + (size_t)gy * w + gx0;
+          float2* dst = reinterpret_cast<float2*>(flow_out) + oi;
+          if (gx0 + 3 < w && (oi & 1) == 0 && (reinterpret_cast<uintptr_t>(flow_out) & 15) == 0) {
+            reinterpret_cast<float4*>(dst)[0] = make_float4(f[0].x, f[0].y, f[1].x, f[1].y);
+            reinterpret_cast<float4*>(dst)[1] = make_float4(f[2].x, f[2].y, f[3].x, f[3].y);
+          } else {
+#pragma unroll
+            for (int o = 0; o < 4; ++o) if (gx0 + o < w) dst[o] = f[o];
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
 // ---- (f) flow upsample between levels: resize(prev, (w,h), INTER_LINEAR) * 2.  One thread per column walks UP_ROWS
 // rows: the column's source coordinates (double, as cv::resize computes them) are evaluated once, the rows' once per
 // block into shared memory.
@@ -1071,6 +1301,8 @@ int flow_init_device_attrs() {
   VQA_CUDA(cudaFuncSetAttribute(k4_flow_iter_march<true, true, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, ms_smem(256)));
   VQA_CUDA(cudaFuncSetAttribute(k4_flow_iter_march<false, true, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, ms_smem(256)));
   VQA_CUDA(cudaFuncSetAttribute(k4_flow_iter_march<true, true, 192>, cudaFuncAttributeMaxDynamicSharedMemorySize, ms_smem(192)));
+  VQA_CUDA(cudaFuncSetAttribute(k4_flow_iter_march3<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, m2_smem()));
+  VQA_CUDA(cudaFuncSetAttribute(k4_flow_iter_march3<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, m2_smem()));
   VQA_CUDA(cudaFuncSetAttribute(k4_pyr_level<0, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
   VQA_CUDA(cudaFuncSetAttribute(k4_pyr_level<3, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
   VQA_CUDA(cudaFuncSetAttribute(k4_pyr_level<9, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
@@ -1159,7 +1391,9 @@ extern "C" int b200vqa_farneback(b200vqa_t* h, const uint8_t* gray0, const uint8
         else { VQA_CUDA(cudaEventCreate(&ev.first)); VQA_CUDA(cudaEventCreate(&ev.second)); }
         VQA_CUDA(cudaEventRecord(ev.first, st));
       }
-      if (h->flow_impl == 0) k4_flow_iter_march<true, true, 256><<<gmarch, 256, ms_smem(256), st>>>(RA0, RB0, RA1, RB1, fin, L.h, L.w, rows_per_seg, fout);
+      if (h->flow_impl == 4) k4_flow_iter_march3<false><<<gmarch, M2_NT, m2_smem(), st>>>(RA0, RB0, RA1, RB1, fin, L.h, L.w, rows_per_seg, fout);
+      else if (h->flow_impl == 5) k4_flow_iter_march3<true><<<gmarch, M2_NT, m2_smem(), st>>>(RA0, RB0, RA1, RB1, fin, L.h, L.w, rows_per_seg, fout);
+      else if (h->flow_impl == 0) k4_flow_iter_march<true, true, 256><<<gmarch, 256, ms_smem(256), st>>>(RA0, RB0, RA1, RB1, fin, L.h, L.w, rows_per_seg, fout);
       else if (h->flow_impl == 3) k4_flow_iter_march<true, true, 192><<<gmarch, 192, ms_smem(192), st>>>(RA0, RB0, RA1, RB1, fin, L.h, L.w, rows_per_seg, fout);
       else if (h->flow_impl == 1) k4_flow_iter_march<false, true, 256><<<gmarch, 256, ms_smem(256), st>>>(RA0, RB0, RA1, RB1, fin, L.h, L.w, rows_per_seg, fout);
       else k4_flow_iter<<<gbox, 256, BX_SMEM, st>>>(RA0, RB0, RA1, RB1, fin, L.h, L.w, fout);

@@ -112,7 +112,57 @@ int launch_gemm_2cta(const CUtensorMap& map_a, const CUtensorMap& map_b, int M, 
   return B200VQA_OK;
 }
 
+int launch_gemm_4cta(const CUtensorMap& map_a, const CUtensorMap& map_b64, int M, int N, int K, const float* bias, const float* residual,
+                     void* out, int out_is_f32, int act, int sm_count, cudaStream_t st) {
+  if (N % G2_BN || K % GEMM_BK || M <= 0) return B200VQA_EINVAL;
+  Gemm2Params p{};
+  p.m2_tiles = cdiv(M, 256); p.n_tiles = N / G2_BN; p.k_blocks = K / GEMM_BK;
+  const size_t fixed = (2 * GEMM_MAX_STAGES + 4) * 8 + 16 + (size_t)GEMM_EPI_WARPS * 32 * EPI_LD * 4 + 1024;
+  p.stages = (int)((227 * 1024 - fixed) / G2_STAGE_BYTES);
+  if (p.stages > GEMM_MAX_STAGES) p.stages = GEMM_MAX_STAGES;
+  if (const char* e = getenv("B200VQA_GEMM_STAGES")) { int v = atoi(e); if (v >= 2 && v <= p.stages) p.stages = v; }
+  p.raster = 8;
+  if (const char* e = getenv("B200VQA_GEMM_RASTER")) p.raster = atoi(e);
+  p.act = act; p.M = M; p.N = N; p.ldo = N; p.out_is_f32 = out_is_f32; p.bias = bias; p.residual = residual; p.out = out;
+  const size_t smem = (size_t)p.stages * G2_STAGE_BYTES + fixed;
+  const int tiles = ((p.m2_tiles + 1) / 2) * p.n_tiles;
+  // resident 4-CTA clusters of this device (33 on a 148-SM B200), optionally capped by the context's SM budget
+  static int max_clusters[64] = {};
+  int dev = 0; VQA_CUDA(cudaGetDevice(&dev));
+  if (dev < 64 && max_clusters[dev] == 0) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(4 * 64); cfg.blockDim = dim3(GEMM_THREADS); cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute at[1]; at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 4; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    int n = 0;
+    VQA_CUDA(cudaOccupancyMaxActiveClusters(&n, gemm4cta_tcgen05_kernel, &cfg));
+    max_clusters[dev] = n > 0 ? n : 1;
+  }
+  int clusters = dev < 64 ? max_clusters[dev] : sm_count / 4;
+  if (clusters > sm_count / 4) clusters = sm_count / 4;
+  if (clusters > tiles) clusters = tiles;
+  if (clusters < 1) clusters = 1;
+  b200vqa_ctx* ctx = g_ctx;
+  std::pair<cudaEvent_t, cudaEvent_t> ev{};
+  const bool prof = ctx && ctx->profiling;
+  if (prof) {
+    if (!ctx->prof_pool.empty()) { ev = ctx->prof_pool.back(); ctx->prof_pool.pop_back(); }
+    else { VQA_CUDA(cudaEventCreate(&ev.first)); VQA_CUDA(cudaEventCreate(&ev.second)); }
+    VQA_CUDA(cudaEventRecord(ev.first, st));
+  }
+  gemm4cta_tcgen05_kernel<<<4 * clusters, GEMM_THREADS, smem, st>>>(map_a, map_b64, p);
+  if (prof) {
+    VQA_CUDA(cudaEventRecord(ev.second, st));
+    ctx->prof_events.push_back(ev);
+    ctx->prof_flops += 2.0 * M * (double)N * K;
+  }
+  VQA_LAUNCH_CHECK();
+  return B200VQA_OK;
+}
+
 int gemm_init_device_attrs() {
+  VQA_CUDA(cudaFuncSetAttribute(gemm4cta_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   VQA_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   VQA_CUDA(cudaFuncSetAttribute(gemm2cta_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   return B200VQA_OK;
@@ -166,6 +216,15 @@ extern "C" int b200vqa_gemm_f16(b200vqa_t* h, const void* A, const void* B, cons
     if ((rc2 = make_tmap_f16(&ma2, A, 2, da2, sa2, box2, nullptr))) return rc2;
     if ((rc2 = make_tmap_f16(&mb2, B, 2, db2, sa2, box2, nullptr))) return rc2;
     return launch_gemm_2cta(ma2, mb2, M, N, K, bias, nullptr, D, 1, ACT_NONE, gemm_grid_sms(h), st);
+  }
+  if (impl == 3) {
+    CUtensorMap ma4, mb4;
+    uint64_t da4[2] = {(uint64_t)K, (uint64_t)M}, db4[2] = {(uint64_t)K, (uint64_t)N}, sa4[1] = {(uint64_t)K * 2};
+    uint32_t boxa4[2] = {GEMM_BK, GEMM_BM}, boxb4[2] = {GEMM_BK, 64};
+    int rc4;
+    if ((rc4 = make_tmap_f16(&ma4, A, 2, da4, sa4, boxa4, nullptr))) return rc4;
+    if ((rc4 = make_tmap_f16(&mb4, B, 2, db4, sa4, boxb4, nullptr))) return rc4;
+    return launch_gemm_4cta(ma4, mb4, M, N, K, bias, nullptr, D, 1, ACT_NONE, gemm_grid_sms(h), st);
   }
   int bn = N >= 256 ? 256 : ((N + 15) / 16) * 16;
   if (const char* e = getenv("B200VQA_GEMM_BN")) { int v = atoi(e); if (v >= 16 && v <= 256 && v % 16 == 0) bn = v; }

@@ -766,6 +766,155 @@ gemm2cta_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
   }
 }
 
+
+// =====================================================================================================
+// 4-CTA variant (two SM pairs per cluster, TMA multicast of the weight tile) - A/B ONLY, measured slower (below).
+// Hypothesis tested: the linears of the ViT are bound by the L2 -> SM operand stream (32 KB per K-block and SM).  Here the
+// two pairs of a cluster compute two vertically adjacent 256 x 256 tiles (row-tile pairs 2 m4 and 2 m4 + 1, same 256
+// weight rows): a CTA (pair p, position r) loads its own 128 rows of A and only a QUARTER of the weight tile (64 rows),
+// multicast to the CTA with the same position in the other pair - 24 KB instead of 32 KB requested from L2 per K-block.
+// Protocol on top of the 2-CTA kernel's: every multicast lands on the full barrier of the destination's pair leader
+// (cta_group::2 TMA, peer bit cleared), whose expected byte count is unchanged (2 x 16 KB of A + 4 x 8 KB of B); a
+// producer may only refill a stage when BOTH pairs have retired the MMAs that read it (it writes into the other pair's
+// shared memory too), so the empty barriers count two arrivals and each leader's tcgen05.commit is multicast to all
+// four CTAs.  The pairs therefore advance in lockstep.  Results are bit-identical to the 2-CTA kernel's.
+// MEASURED (round 2, tools/gemm_mc_ab.py, 264 images, L2 flushed): a B200 keeps only 33 such clusters resident (132 of
+// 148 SMs: tools/probes/cluster_probe.cu) and the kernel runs at exactly that ratio - 8192^3: 1115 vs 1252 TFLOP/s (0.89);
+// qkv 774 vs 809, proj 595 vs 606, fc1 801 vs 830, fc2 905 vs 1054.  So the operand stream from L2 is NOT the bound (the
+// L2 already serves both pairs' requests for the same lines once: multicast saves nothing below 8 CTAs); what the SM
+// pays per K-block is unchanged - 32 KB written into and 32 KB read out of its shared memory in the 512 clk of the MMAs.
+constexpr uint32_t G4_BQ_BYTES = 64 * GEMM_BK * 2;                    // one multicast quarter of the B tile: 64 rows x 64 fp16
+__device__ __forceinline__ void tma_load_2d_2sm_mc(const CUtensorMap* map, uint32_t leader_bar, void* dst, int c0, int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void tcgen05_commit_2sm_mask(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+
+__global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+gemm4cta_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b64, const Gemm2Params p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t a_bytes = GEMM_BM * GEMM_BK * 2;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * G2_STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + GEMM_MAX_STAGES;
+  uint64_t* tmem_full = empty_bar + GEMM_MAX_STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  float* epi_stage = reinterpret_cast<float*>(tmem_slot + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();                 // 0..3
+  const uint32_t pair = rank >> 1, pos = rank & 1;         // pair of the cluster, position in the pair (0 = leader)
+  const int m4_tiles = (p.m2_tiles + 1) >> 1;
+  const int num_tiles = m4_tiles * p.n_tiles;
+  const int cluster_id = blockIdx.x >> 2, num_clusters = gridDim.x >> 2;
+  Gemm2Params q = p; q.m2_tiles = m4_tiles; q.raster = p.raster > 1 ? p.raster >> 1 : p.raster;   // raster groups in units of two row-tile pairs
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b64) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < p.stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 2); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 2 * GEMM_EPI_WARPS); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(GEMM_TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================= TMA producer (all four CTAs): own A rows + one multicast quarter of the B rows =================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      const uint16_t bmask = (uint16_t)((1u << pos) | (1u << (2 + pos)));       // the CTAs at my position in both pairs
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        int m4, nt; g2_tile_coords(q, tile, m4, nt);
+        const int m2 = 2 * m4 + (int)pair;
+        for (int kb = 0; kb < p.k_blocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + (size_t)stage * G2_STAGE_BYTES;
+          uint8_t* sb = sa + a_bytes;
+          if (pos == 0) mbar_expect_tx(&full_bar[stage], 2 * G2_STAGE_BYTES);      // bytes of both CTAs of the pair land on its leader's barrier
+          const uint32_t leader_bar = smem_u32(&full_bar[stage]) & 0xFEFFFFFFu;
+          tma_load_2d_2sm(&map_a, leader_bar, sa, kb * GEMM_BK, m2 * 256 + (int)pos * GEMM_BM);
+          tma_load_2d_2sm_mc(&map_b64, leader_bar, sb + pair * G4_BQ_BYTES, kb * GEMM_BK, nt * G2_BN + (int)pos * 128 + (int)pair * 64, bmask);
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer (the leader of each pair) =================
+    if (pos == 0) {
+      const uint32_t idesc = (1u << 4) | ((uint32_t)(G2_BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+      const uint16_t pair_mask = (uint16_t)(3u << (2 * pair));
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        if (lane == 0) mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        __syncwarp();
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)acc * 256u;
+        for (int kb = 0; kb < p.k_blocks; ++kb) {
+          if (lane == 0) {
+            mbar_wait(&full_bar[stage], phase);
+            tcgen05_fence_after();
+            const uint32_t sa = smem_u32(smem + (size_t)stage * G2_STAGE_BYTES);
+            const uint64_t adesc = make_smem_desc(sa), bdesc = make_smem_desc(sa + a_bytes);
+#pragma unroll
+            for (int k = 0; k < GEMM_BK / 16; ++k)
+              tcgen05_mma_f16_2sm(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+            tcgen05_commit_2sm_mask(&empty_bar[stage], (uint16_t)0xF);      // the stage is refilled by CTAs of both pairs
+            if (kb == p.k_blocks - 1) tcgen05_commit_2sm_mask(&tmem_full[acc], pair_mask);
+          }
+          __syncwarp();
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ================= epilogue (all four CTAs): own 128 rows x 256 columns =================
+    const int qd = warp & 3, grp = (warp - 4) >> 2;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+      int m4, nt; g2_tile_coords(q, tile, m4, nt);
+      const int m2 = 2 * m4 + (int)pair;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tcgen05_fence_after();
+      const uint32_t taddr = tmem_base + (uint32_t)acc * 256u + ((uint32_t)(qd * 32) << 16);
+      if (!p.out_is_f32 && !p.residual && (p.ldo & 15) == 0) {
+        epi_row_direct_f16(p.bias, static_cast<__half*>(p.out), p.M, p.ldo, p.act, G2_BN, taddr,
+                           m2 * 256 + (int)pos * GEMM_BM + qd * 32 + lane, nt * G2_BN, grp);
+      } else {
+        epi_row_fast(p.bias, p.residual, p.out, p.M, p.ldo, p.out_is_f32, p.act, G2_BN, taddr, epi_stage + (warp - 4) * (32 * EPI_LD),
+                     m2 * 256 + (int)pos * GEMM_BM + qd * 32, nt * G2_BN, grp, lane);
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(&tmem_empty[acc], rank & ~1u);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tcgen05_fence_before();
+  cluster_sync_all();                      // no CTA may exit (or free TMEM) while a peer can still write into it or signal it
+  if (warp == 2) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(GEMM_TMEM_COLS) : "memory");
+  }
+}
+
 #endif  // B200VQA_GEMM_KERNEL_TU
 
 inline size_t gemm_smem_bytes(int block_n, int stages) {
@@ -791,6 +940,9 @@ int pick_stages(int block_n);
 // 2-CTA (cta_group::2) linear layer: out[M][N] = act(A[M][K] W[N][K]^T + bias) (+ residual); N % 256 == 0, K % 64 == 0.
 // map_a / map_b must be built with 128-row boxes.
 int launch_gemm_2cta(const CUtensorMap& map_a, const CUtensorMap& map_b, int M, int N, int K, const float* bias, const float* residual,
+                     void* out, int out_is_f32, int act, int sm_count, cudaStream_t st);
+// 4-CTA clusters with the weight tile multicast between two SM pairs; map_b64 must be built with 64-row boxes.
+int launch_gemm_4cta(const CUtensorMap& map_a, const CUtensorMap& map_b64, int M, int N, int K, const float* bias, const float* residual,
                      void* out, int out_is_f32, int act, int sm_count, cudaStream_t st);
 
 // SIMT check kernels (gemm_ref.cuh), launched from other translation units through these wrappers

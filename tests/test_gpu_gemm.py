@@ -49,3 +49,23 @@ def test_gemm_2cta_matches_fp32_reference(ctx, mnk):
     torch.cuda.synchronize()
     tol = 1e-5 * K ** 0.5 * 4 + 1e-6
     assert (got - ref).abs().max().item() <= max(tol, 1e-4), mnk
+
+
+@pytest.mark.parametrize("mnk", [(256, 256, 64), (512, 768, 768), (700, 256, 128), (197 * 5, 2304, 768), (1000, 768, 3072), (300, 3072, 768),
+                                 (197 * 40, 768, 768)])
+def test_gemm_4cta_matches_fp32_reference(ctx, mnk):
+    """4-CTA clusters: two SM pairs, the weight tile multicast between them (odd numbers of row-tile pairs leave the second
+    pair of the last cluster on zero-filled rows)."""
+    from relax_vqa_b200 import ops
+    M, N, K = mnk
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    A = (torch.randn(M, K, device="cuda", generator=g) * 0.5).half()
+    B = (torch.randn(N, K, device="cuda", generator=g) * 0.5).half()
+    bias = torch.randn(N, device="cuda", generator=g)
+    ref = A.float() @ B.float().t() + bias
+    got = ops.gemm_f16(ctx, A, B, bias, impl=3)
+    torch.cuda.synchronize()
+    tol = 1e-5 * K ** 0.5 * 4 + 1e-6
+    assert (got - ref).abs().max().item() <= max(tol, 1e-4), mnk
+    two = ops.gemm_f16(ctx, A, B, bias, impl=2)
+    assert torch.equal(got, two), "same MMA order per tile as the 2-CTA kernel: results must be bit-identical"

@@ -140,6 +140,153 @@ k4_pyr_level(const uint8_t* __restrict__ gray0, const uint8_t* __restrict__ gray
   }
 }
 
+// ---- (a+b), fused streaming form for the exact power-of-two levels (W % 8 == 0 and H, W divisible by the level's scale
+// S = 2, 4, 8: 1080p, 2160p, 720p ...).  There the bilinear taps of cv::resize sit at columns / rows S x + S/2 - 1 and + 1
+// with weights 0.5 / 0.5.  One thread owns 8 source columns (= 4 / 2 / 1 output columns of levels 1 / 2 / 3) and marches
+// down the source rows of a segment: per row it loads its 24-byte window once (3 x LDG.64, coalesced across the warp),
+// runs the horizontal Gaussian at the left and right tap column of each of its outputs, for all three levels, and adds
+// the two values into the (at most three) pending output rows per level whose vertical windows contain the row, with
+// compile-time tap indices.  The arithmetic is k4_pyr_level's, operation for operation (taps in ascending order from a
+// zero accumulator, the four Gaussian values of an output kept apart until the bilinear combination), so the two kernels
+// agree bit for bit - which matters: on static scenes the flow near the image border is decided by the SIGN of a ~1e-6 px
+// displacement (in / out of bounds in UpdateMatrices), and a variant with folded taps (half the arithmetic, values equal
+// to 3e-7 relative) moved single border pixels by 0.06 px away from OpenCV.
+// The full-resolution frames are read once for the three levels; the tile kernel reads them once per level, stages them
+// through shared memory byte by byte and runs at a tenth of its HBM roofline (461 us per 22 pairs of 1080p; this: see
+// profiles/).
+struct PyrFusedTaps { float t1[3], t2[9], t3[19]; };
+constexpr int PF_NT = 128;                         // threads per block: 4 warps x 32 column groups x 8 source pixels
+
+// pending output rows of one level.  S = stride, KS = Gaussian size, NO = 8 / S output columns per thread.
+// v[o][slot][.] = Gaussian at (upper row, left col), (upper, right), (lower, left), (lower, right) of the bilinear cell
+template <int S, int KS, int NO>
+struct PyrAcc {
+  float v[NO][3][4];                               // slots: output rows m - 1, m, m + 1 (m = current period)
+  __device__ __forceinline__ void clear() {
+#pragma unroll
+    for (int o = 0; o < NO; ++o)
+#pragma unroll
+      for (int sl = 0; sl < 3; ++sl) v[o][sl][0] = v[o][sl][1] = v[o][sl][2] = v[o][sl][3] = 0.f;
+  }
+  // source row with phase I (= row index mod S, compile-time after unrolling); hl / hr = horizontal Gaussian at the left /
+  // right tap column of each output
+  __device__ __forceinline__ void add(int I, const float (&hl)[NO], const float (&hr)[NO], const float* T) {
+#pragma unroll
+    for (int d = -1; d <= 1; ++d) {
+      const int k0 = I - (S / 2 - 1) + (KS >> 1) - S * d, k1 = k0 - 1;       // tap index in the upper / lower row's window
+#pragma unroll
+      for (int o = 0; o < NO; ++o) {
+        if (k0 >= 0 && k0 < KS) { v[o][d + 1][0] = fmaf(T[k0], hl[o], v[o][d + 1][0]); v[o][d + 1][1] = fmaf(T[k0], hr[o], v[o][d + 1][1]); }
+        if (k1 >= 0 && k1 < KS) { v[o][d + 1][2] = fmaf(T[k1], hl[o], v[o][d + 1][2]); v[o][d + 1][3] = fmaf(T[k1], hr[o], v[o][d + 1][3]); }
+      }
+    }
+  }
+  static __device__ __forceinline__ bool completes(int I) { return I - (S / 2 - 1) + (KS >> 1) + S == KS; }   // row m - 1 got its last tap
+  __device__ __forceinline__ float result(int o) const {                   // cv::resize with both weights 0.5
+    const float top = fmaf(v[o][0][0], 0.5f, v[o][0][1] * 0.5f), bot = fmaf(v[o][0][2], 0.5f, v[o][0][3] * 0.5f);
+    return fmaf(top, 0.5f, bot * 0.5f);
+  }
+  __device__ __forceinline__ void rotate() {
+#pragma unroll
+    for (int o = 0; o < NO; ++o)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) { v[o][0][c] = v[o][1][c]; v[o][1][c] = v[o][2][c]; v[o][2][c] = 0.f; }
+  }
+};
+
+__device__ __forceinline__ uint32_t u2_byte(const uint2& v, int j) { return ((j < 4 ? v.x : v.y) >> (8 * (j & 3))) & 0xffu; }
+
+// horizontal Gaussian of KS taps starting at window position p0 (k4_pyr_level's order: ascending, from a zero accumulator)
+template <int KS>
+__device__ __forceinline__ float pyr_hsum(const float* T, const float (&f)[24], int p0) {
+  float acc = T[0] * f[p0];
+#pragma unroll
+  for (int k = 1; k < KS; ++k) acc = fmaf(T[k], f[p0 + k], acc);
+  return acc;
+}
+
+template <int MASK>                                 // bit l - 1 set: level l is produced by this instantiation
+__global__ void __launch_bounds__(PF_NT)
+k4_pyr_fused(const uint8_t* __restrict__ gray0, const uint8_t* __restrict__ gray1, int B, int H, int W, PyrFusedTaps tp, int os3,
+             float* __restrict__ I1, float* __restrict__ I2, float* __restrict__ I3) {
+  const int G = W >> 3;                                              // column groups of 8 source pixels
+  const int g = blockIdx.x * PF_NT + threadIdx.x;
+  if (g >= G) return;
+  const int z = blockIdx.z;
+  const uint8_t* img = (z < B ? gray0 + (size_t)z * H * W : gray1 + (size_t)(z - B) * H * W);
+  const int a3 = blockIdx.y * os3, b3 = min(a3 + os3, (H + 7) >> 3);   // this segment's output rows in level-3 units (8 source rows)
+  const int gA = max(g - 1, 0), gC = min(g + 1, G - 1);
+  PyrAcc<2, 3, 4> L1; PyrAcc<4, 9, 2> L2; PyrAcc<8, 19, 1> L3;
+  L1.clear(); L2.clear(); L3.clear();
+  const int h1 = H >> 1, w1 = W >> 1, h2 = H >> 2, w2 = W >> 2, h3 = H >> 3, w3 = W >> 3;
+  for (int M = a3 - 1; M <= b3; ++M) {                               // periods of 8 source rows; M - 1 = the level-3 row that completes in it
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int y = reflect101(8 * M + i, H);
+      const uint2* row = reinterpret_cast<const uint2*>(img + (size_t)y * W);
+      uint2 wa = __ldg(row + gA), wb = __ldg(row + g), wc = __ldg(row + gC);
+      if (g == 0) {                                                  // x = -j -> j (REFLECT_101): positions 0..7 of the window
+        uint2 n = make_uint2(0u, 0u);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const uint32_t bb = q == 0 ? u2_byte(wc, 0) : u2_byte(wb, 8 - q);
+          if (q < 4) n.x |= bb << (8 * q); else n.y |= bb << (8 * (q - 4));
+        }
+        wa = n;
+      }
+      if (g == G - 1) {                                              // x = W + j -> W - 2 - j: positions 16..23
+        uint2 n = make_uint2(0u, 0u);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const uint32_t bb = q == 7 ? u2_byte(wa, 7) : u2_byte(wb, 6 - q);
+          if (q < 4) n.x |= bb << (8 * q); else n.y |= bb << (8 * (q - 4));
+        }
+        wc = n;
+      }
+      // bytes 2..22 of the window as floats (2^23 + b through one byte permute, minus 2^23)
+      float f[24];
+      const uint32_t wd[6] = {wa.x, wa.y, wb.x, wb.y, wc.x, wc.y};
+#pragma unroll
+      for (int pz = 2; pz <= 22; ++pz)
+        f[pz] = __uint_as_float(__byte_perm(wd[pz >> 2], 0x4B000000u, 0x7650u + (pz & 3))) - 8388608.0f;
+      if (MASK & 1) {                                                // outputs 4 g + o: left tap column 8 g + 2 o, window from 2 o - 1
+        float hl[4], hr[4];
+#pragma unroll
+        for (int o = 0; o < 4; ++o) { hl[o] = pyr_hsum<3>(tp.t1, f, 7 + 2 * o); hr[o] = pyr_hsum<3>(tp.t1, f, 8 + 2 * o); }
+        L1.add(i & 1, hl, hr, tp.t1);
+        if (PyrAcc<2, 3, 4>::completes(i & 1)) {
+          const int yo = (4 * M + (i >> 1)) - 1;
+          if (yo >= 4 * a3 && yo < min(4 * b3, h1))
+            *reinterpret_cast<float4*>(I1 + ((size_t)z * h1 + yo) * w1 + 4 * g) = make_float4(L1.result(0), L1.result(1), L1.result(2), L1.result(3));
+        }
+        if ((i & 1) == 1) L1.rotate();
+      }
+      if (MASK & 2) {                                                // outputs 2 g + o: left tap column 8 g + 4 o + 1, window from 4 o - 3
+        float hl[2], hr[2];
+#pragma unroll
+        for (int o = 0; o < 2; ++o) { hl[o] = pyr_hsum<9>(tp.t2, f, 5 + 4 * o); hr[o] = pyr_hsum<9>(tp.t2, f, 6 + 4 * o); }
+        L2.add(i & 3, hl, hr, tp.t2);
+        if (PyrAcc<4, 9, 2>::completes(i & 3)) {
+          const int yo = (2 * M + (i >> 2)) - 1;
+          if (yo >= 2 * a3 && yo < min(2 * b3, h2))
+            *reinterpret_cast<float2*>(I2 + ((size_t)z * h2 + yo) * w2 + 2 * g) = make_float2(L2.result(0), L2.result(1));
+        }
+        if ((i & 3) == 3) L2.rotate();
+      }
+      if (MASK & 4) {                                                // output g: left tap column 8 g + 3, window from -6
+        float hl[1], hr[1];
+        hl[0] = pyr_hsum<19>(tp.t3, f, 2); hr[0] = pyr_hsum<19>(tp.t3, f, 3);
+        L3.add(i, hl, hr, tp.t3);
+        if (PyrAcc<8, 19, 1>::completes(i)) {
+          const int yo = M - 1;
+          if (yo >= a3 && yo < min(b3, h3)) I3[((size_t)z * h3 + yo) * w3 + g] = L3.result(0);
+        }
+        if (i == 7) L3.rotate();
+      }
+    }
+  }
+}
+
 // ---- (c) polynomial expansion: I -> R.  Tile 64 x 16 outputs, halo 5; each thread produces 4 consecutive
 // values per pass from a 14-value register window (3x fewer shared-memory loads than one value per thread).
 // R layout: RA [img][h][w] float4 = (y, x, yy, xx) coefficients, RB [img][h][w] float = xy coefficient.
@@ -1322,17 +1469,56 @@ extern "C" int b200vqa_farneback(b200vqa_t* h, const uint8_t* gray0, const uint8
   const size_t P = (size_t)H * W;
   // workspace (float units): RA [2B][P] float4 | RB [2B][P] | I [2B][P/4] (levels >= 1 only) | flowA, flowB [B][P][2]
   const std::vector<Level> plan = pyramid_plan(H, W);
+  // I: one image pair per coarser level (the fused pyramid kernel writes all of them before the first level runs)
+  std::vector<size_t> ioff(plan.size(), 0);
   size_t Pq = 16;
-  for (size_t li = 0; li + 1 < plan.size(); ++li) Pq = std::max(Pq, (size_t)plan[li].h * plan[li].w);
-  if (plan.size() == 1) Pq = P;
-  const size_t floats = (size_t)B * (P * (8 + 2 + 4) + Pq * 2) + 64;
+  for (size_t li = 0; li + 1 < plan.size(); ++li) { ioff[li] = Pq; Pq += (((size_t)plan[li].h * plan[li].w * 2 * B) + 15) & ~(size_t)15; }
+  const size_t floats = (size_t)B * P * (8 + 2 + 4) + Pq + 64;
   int rc = h->ws_flow.reserve(floats * sizeof(float));
   if (rc) return rc;
   float4* RA = static_cast<float4*>(h->ws_flow.ptr);
   float* RB = reinterpret_cast<float*>(RA + 2 * (size_t)B * P);
   float* flowA = RB + 2 * (size_t)B * P;
   float* flowB = flowA + 2 * (size_t)B * P;
-  float* I = flowB + 2 * (size_t)B * P;
+  float* Ibase = flowB + 2 * (size_t)B * P;
+  // levels with an exact power-of-two scale are filtered by ONE pass of k4_pyr_fused over the full-resolution frames
+  bool fused[4] = {false, false, false, false};                   // index = log2(scale)
+  static const bool pyr_tile = getenv("B200VQA_PYR_TILE") != nullptr;        // A/B: tile kernel for every level
+  if (!pyr_tile && h->flow_impl != 2 && (W & 7) == 0 && ((reinterpret_cast<uintptr_t>(gray0) | reinterpret_cast<uintptr_t>(gray1)) & 7) == 0) {
+    float* Il[4] = {nullptr, nullptr, nullptr, nullptr};
+    PyrFusedTaps ft{};
+    for (size_t li = 0; li + 1 < plan.size(); ++li) {
+      const Level& L = plan[li];
+      const int lg = (int)(plan.size() - 1 - li);                 // log2(1 / scale)
+      const int S = 1 << lg;
+      if (lg < 1 || lg > 3 || H % S || W % S || L.h != H / S || L.w != W / S || L.ksize != (lg == 1 ? 3 : (lg == 2 ? 9 : 19))) continue;
+      const Taps t = gaussian_taps(L.ksize, L.sigma);
+      float* dst = lg == 1 ? ft.t1 : (lg == 2 ? ft.t2 : ft.t3);
+      for (int k = 0; k < L.ksize; ++k) dst[k] = t.t[k];
+      fused[lg] = true;
+      Il[lg] = Ibase + ioff[li];
+    }
+    // too few threads for a streaming kernel (short clips of small frames): the tile kernel is as fast there
+    const int G = W >> 3, p3 = (H + 7) >> 3;
+    int os3 = 0;
+    for (int cand : {15, 8, 4}) if (!os3 && (long)2 * B * G * cdiv(p3, cand) >= 40000) os3 = cand;
+    if (const char* e = getenv("B200VQA_PYR_OS3")) os3 = atoi(e);
+    if (!os3) fused[1] = fused[2] = fused[3] = false;
+    const int mask = (fused[1] ? 1 : 0) | (fused[2] ? 2 : 0) | (fused[3] ? 4 : 0);
+    static const bool pyr_split = getenv("B200VQA_PYR_SPLIT") != nullptr;      // A/B: level 1 in its own launch (fewer registers each)
+    const dim3 gf(cdiv(G, PF_NT), cdiv(p3, os3 ? os3 : 1), 2 * B);
+#define PYR_FUSED_LAUNCH(M) k4_pyr_fused<M><<<gf, PF_NT, 0, st>>>(gray0, gray1, B, H, W, ft, os3, Il[1], Il[2], Il[3])
+    if (mask == 7 && pyr_split) { PYR_FUSED_LAUNCH(1); VQA_LAUNCH_CHECK(); PYR_FUSED_LAUNCH(6); VQA_LAUNCH_CHECK(); }
+    else if (mask) {
+      switch (mask) {
+        case 1: PYR_FUSED_LAUNCH(1); break; case 2: PYR_FUSED_LAUNCH(2); break; case 3: PYR_FUSED_LAUNCH(3); break;
+        case 4: PYR_FUSED_LAUNCH(4); break; case 5: PYR_FUSED_LAUNCH(5); break; case 6: PYR_FUSED_LAUNCH(6); break;
+        default: PYR_FUSED_LAUNCH(7); break;
+      }
+      VQA_LAUNCH_CHECK();
+    }
+#undef PYR_FUSED_LAUNCH
+  }
   static const PolyConsts pc = poly_consts();
   static const bool poly_tile = getenv("B200VQA_POLY_TILE") != nullptr;      // A/B: 64 x 16 tile expansion kernel
   float* prev = nullptr;         // flow of the previous (coarser) level
@@ -1352,6 +1538,9 @@ extern "C" int b200vqa_farneback(b200vqa_t* h, const uint8_t* gray0, const uint8
       else k4_polyexp_march<true><<<gpoly, PM_NT, 0, st>>>(nullptr, gray0, gray1, B, L.h, L.w, poly_rows, pc, RA, RB);
       VQA_LAUNCH_CHECK();
     } else {
+      float* I = Ibase + ioff[li];
+      const int lg = (int)(plan.size() - 1 - li);
+      if (!(lg >= 1 && lg <= 3 && fused[lg])) {
       const double sx = (double)W / L.w, sy = (double)H / L.h;
       // shared-memory window: uint8 source tile + f32 horizontally blurred columns
       const int TY = L.ksize == 3 ? 32 : (L.ksize == 9 ? 16 : 8);
@@ -1364,6 +1553,7 @@ extern "C" int b200vqa_farneback(b200vqa_t* h, const uint8_t* gray0, const uint8
       else if (L.ksize == 19) k4_pyr_level<19, 8><<<gpyr, 256, smem, st>>>(gray0, gray1, B, H, W, taps, L.h, L.w, sx, sy, I);
       else k4_pyr_level<0, 8><<<gpyr, 256, smem, st>>>(gray0, gray1, B, H, W, taps, L.h, L.w, sx, sy, I);
       VQA_LAUNCH_CHECK();
+      }
       // I holds [2B][h][w]; expansion of images 0..B-1 then B..2B-1 (contiguous)
       if (h->flow_impl == 2 || poly_tile) k4_polyexp<false><<<dim3(cdiv(L.w, PE_TW), cdiv(L.h, PE_TH), 2 * B), 256, 0, st>>>(I, nullptr, nullptr, B, L.h, L.w, pc, RA, RB);
       else k4_polyexp_march<false><<<gpoly, PM_NT, 0, st>>>(I, nullptr, nullptr, B, L.h, L.w, poly_rows, pc, RA, RB);

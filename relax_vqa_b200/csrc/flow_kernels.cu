@@ -1314,6 +1314,53 @@ k5_flow_rgb_patchsum(const float* __restrict__ flow, int H, int W, const float* 
   }
 }
 
+// Same outputs, warp-per-band form (default): one warp colours a band of 128 pixels x 16 rows (8 patches), each lane 4
+// consecutive pixels per row (two 16-byte loads), and keeps its part of the patch sums in a register over the 16 rows:
+// two shuffles per patch instead of four per pixel row, no shared memory, no atomics, no block barrier (the 64 x 16 block
+// form above stalls all 1024 threads on the two f64 divisions of the normalisation constants: 372 us per 22 pairs of
+// 1080p against a 57 us read of the flow).  The constants are computed by lane 0 of every warp and broadcast.
+constexpr int RG_WARPS = 8;
+__global__ void __launch_bounds__(RG_WARPS * 32)
+k5_flow_rgb_patchsum_band(const float* __restrict__ flow, int H, int W, const float* __restrict__ minmax, uint8_t* __restrict__ rgb,
+                          uint32_t* __restrict__ sums) {
+  const int lane = threadIdx.x & 31;
+  const int strip = blockIdx.x * RG_WARPS + (threadIdx.x >> 5);
+  const int x0 = strip * 128 + lane * 4, py = blockIdx.y, b = blockIdx.z;
+  if (strip * 128 >= W) return;                               // whole warp
+  NormConsts nc;
+  if (lane == 0) nc = norm_consts(minmax + 2 * b);
+  nc.a1 = __shfl_sync(0xffffffffu, nc.a1, 0); nc.b1 = __shfl_sync(0xffffffffu, nc.b1, 0);
+  nc.a2 = __shfl_sync(0xffffffffu, nc.a2, 0); nc.b2 = __shfl_sync(0xffffffffu, nc.b2, 0);
+  const int gw = W >> 4, gh = H >> 4;
+  const bool vec = (W & 3) == 0 && x0 + 3 < W && (reinterpret_cast<uintptr_t>(flow) & 15) == 0;
+  uint32_t s = 0;
+#pragma unroll 4
+  for (int r = 0; r < 16; ++r) {
+    const int y = py * 16 + r;
+    if (y >= H) break;
+    const size_t p = ((size_t)b * H + y) * W + x0;
+    float2 d[4];
+    if (vec) {
+      const float4 q0 = __ldg(reinterpret_cast<const float4*>(flow + 2 * p)), q1 = __ldg(reinterpret_cast<const float4*>(flow + 2 * p) + 1);
+      d[0] = make_float2(q0.x, q0.y); d[1] = make_float2(q0.z, q0.w); d[2] = make_float2(q1.x, q1.y); d[3] = make_float2(q1.z, q1.w);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) d[j] = x0 + j < W ? reinterpret_cast<const float2*>(flow)[p + j] : make_float2(0.f, 0.f);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (x0 + j < W) {
+        const uchar3 c = flow_colour(d[j].x, d[j].y, nc);
+        if (rgb) { rgb[(p + j) * 3] = c.x; rgb[(p + j) * 3 + 1] = c.y; rgb[(p + j) * 3 + 2] = c.z; }
+        s += (uint32_t)c.x + c.y + c.z;
+      }
+    }
+  }
+  s += __shfl_xor_sync(0xffffffffu, s, 1);
+  s += __shfl_xor_sync(0xffffffffu, s, 2);                     // 4 lanes = the 16 columns of one patch
+  if (sums && (lane & 3) == 0 && (x0 >> 4) < gw && py < gh) sums[((size_t)b * gh + py) * gw + (x0 >> 4)] = s;
+}
+
 // gather flow-colour patches (recomputed from the flow) and merge with the diff fragment
 __global__ void __launch_bounds__(256)
 k5_flow_fragment_merge(const float* __restrict__ flow, const float* __restrict__ minmax, int H, int W,
@@ -1612,7 +1659,11 @@ extern "C" int b200vqa_flow_to_rgb(const float* flow, int B, int H, int W, uint8
   k5_mag_minmax<<<dim3(gx, B), 256, 0, st>>>(flow, npix, minmax);
   VQA_LAUNCH_CHECK();
   if (rgb || sums) {
-    k5_flow_rgb_patchsum<<<dim3(cdiv(W, 64), cdiv(H, 16), B), dim3(64, 16), 0, st>>>(flow, H, W, minmax, rgb, sums);
+    static const bool rgb_block = getenv("B200VQA_RGB_BLOCK") != nullptr;      // A/B: the 64 x 16 block form
+    // a band = one warp: short clips of small frames do not fill the GPU with bands (273 x 481 x 3: 216 warps), the block form does
+    const long bands = (long)B * cdiv(W, 128) * cdiv(H, 16);
+    if (rgb_block || bands < 2400) k5_flow_rgb_patchsum<<<dim3(cdiv(W, 64), cdiv(H, 16), B), dim3(64, 16), 0, st>>>(flow, H, W, minmax, rgb, sums);
+    else k5_flow_rgb_patchsum_band<<<dim3(cdiv(cdiv(W, 128), RG_WARPS), cdiv(H, 16), B), RG_WARPS * 32, 0, st>>>(flow, H, W, minmax, rgb, sums);
     VQA_LAUNCH_CHECK();
   }
   return B200VQA_OK;

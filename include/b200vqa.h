@@ -96,6 +96,11 @@ int b200vqa_merge_fragments(const uint8_t* a, const uint8_t* b, size_t nbytes, u
  * reverses the channel order on output (cv2 BGR frame -> the RGB image PIL would open). */
 int b200vqa_resize_pil(b200vqa_t* h, const uint8_t* src, int B, int H, int W, int filter,
                        int swap_rb, uint8_t* dst, void* stream);
+/* Both filters of the same frames in one call (every full frame goes to the ResNet through BILINEAR and to the ViT
+ * through LANCZOS: main_fragment_layerstack.py:283-288): the horizontal passes share one read of the source.
+ * Results are those of two b200vqa_resize_pil calls, bit for bit. */
+int b200vqa_resize_pil_pair(b200vqa_t* h, const uint8_t* src, int B, int H, int W, int swap_rb,
+                            uint8_t* dst_bilinear, uint8_t* dst_lanczos, void* stream);
 
 /* ---- A5: cv2.calcOpticalFlowFarneback(g0, g1, None, 0.5, 3, 15, 3, 5, 1.2, 0) (:313-315).
  * gray0/gray1: [B][H][W] uint8; flow: [B][H][W][2] float32 (dx, dy). */

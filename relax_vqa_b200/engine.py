@@ -208,8 +208,7 @@ class Engine:
                     nx_pairs = torch.cat([clips[i].nexts for i in unit])
                     fr_all = torch.cat([clips[i].frames for i in unit])
                 ori, mer = self.fragments(fr_pairs, nx_pairs, ctx=lctx)
-                rn = ops.resize_pil(lctx, fr_all, ops.BILINEAR)
-                vt = ops.resize_pil(lctx, fr_all, ops.LANCZOS)
+                rn, vt = ops.resize_pil_pair(lctx, fr_all)       # BILINEAR for the ResNet, LANCZOS for the ViT
             for t in [ori, mer, rn, vt] + [clips[i].frames for i in unit] + [clips[i].nexts for i in unit]:
                 t.record_stream(s)
                 t.record_stream(main)

@@ -145,6 +145,16 @@ def resize_pil(ctx, src, filt, swap_rb=False):
     return dst
 
 
+def resize_pil_pair(ctx, src, swap_rb=False):
+    """(BILINEAR, LANCZOS) resizes of the same frames in one call: the horizontal passes share one read of the source.
+    Bit-identical to two resize_pil calls."""
+    B, H, W, _ = _u8(src).shape
+    bil = torch.empty((B, TARGET, TARGET, 3), dtype=torch.uint8, device=src.device)
+    lan = torch.empty_like(bil)
+    check(ctx.lib.b200vqa_resize_pil_pair(ctx.h, ptr(src), B, H, W, int(swap_rb), ptr(bil), ptr(lan), stream_ptr(src.device)), "resize_pil_pair")
+    return bil, lan
+
+
 def gemm_f16(ctx, A, Bm, bias=None, impl=0):
     """D = A @ Bm.T + bias; A [M,K], Bm [N,K] fp16 -> fp32 [M,N] (test / profiling entry)."""
     M, K = A.shape

@@ -133,3 +133,18 @@ def test_resize_bit_exact(ctx, wh, filt):
         assert np.array_equal(out[i], R.resize(img[i], 224, 224, filt))
     sw = ops.resize_pil(ctx, _dev(img), filt, swap_rb=True).cpu().numpy()
     assert np.array_equal(sw, out[..., ::-1])
+
+
+@pytest.mark.parametrize("wh", [(960, 540), (1920, 1080), (404, 720), (224, 300), (97, 61), (3840, 2160)])
+def test_resize_pair_equals_two_calls(ctx, wh):
+    """Both filters from one staged read of the source (the engine's call): bit-identical to the two single-filter calls,
+    which test_resize_bit_exact pins to Pillow.  Includes saturated images (extreme accumulator values of the split sums)."""
+    from relax_vqa_b200 import ops
+    rng = np.random.default_rng(wh[0])
+    img = rng.integers(0, 256, (3, wh[1], wh[0], 3), dtype=np.uint8)
+    img[1] = 255
+    img[2] = np.where(rng.random(img[2].shape) < 0.5, 0, 255)
+    for swap in (False, True):
+        bil, lan = ops.resize_pil_pair(ctx, _dev(img), swap_rb=swap)
+        assert torch.equal(bil, ops.resize_pil(ctx, _dev(img), 0, swap_rb=swap))
+        assert torch.equal(lan, ops.resize_pil(ctx, _dev(img), 1, swap_rb=swap))

@@ -106,6 +106,11 @@ int b200vqa_resize_pil_pair(b200vqa_t* h, const uint8_t* src, int B, int H, int 
  * gray0/gray1: [B][H][W] uint8; flow: [B][H][W][2] float32 (dx, dy). */
 int b200vqa_farneback(b200vqa_t* h, const uint8_t* gray0, const uint8_t* gray1, int B, int H,
                       int W, float* flow, void* stream);
+/* A5 + the statistics A6 / A7 need, in one call (:313-319): flow as above, minmax [B][2] = min / max of its magnitude
+ * (reduced by the launch that writes the flow) and sums [B][H/16][W/16] = the 16x16 patch sums of flow_to_rgb(flow).
+ * Results are those of b200vqa_farneback followed by b200vqa_flow_to_rgb(rgb = NULL), bit for bit. */
+int b200vqa_farneback_flow_sums(b200vqa_t* h, const uint8_t* gray0, const uint8_t* gray1, int B,
+                                int H, int W, float* flow, uint32_t* sums, float* minmax, void* stream);
 
 /* ---- A6: flow_to_rgb (:162-175).  rgb (really BGR, like the reference): [B][H][W][3] or NULL.
  * sums (patch sums of the colour image, A7) may be NULL.  minmax: [B][2] float scratch/out. */

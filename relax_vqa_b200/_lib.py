@@ -31,6 +31,7 @@ SIGNATURES = {
     "b200vqa_resize_pil": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "b200vqa_resize_pil_pair": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "b200vqa_farneback": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "b200vqa_farneback_flow_sums": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "b200vqa_flow_to_rgb": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "b200vqa_flow_fragment_merge": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "b200vqa_load_resnet50": (c_int, [c_void_p, c_int, C.POINTER(C.c_char_p), C.POINTER(c_void_p), C.POINTER(c_int64)]),

@@ -736,12 +736,20 @@ __device__ __forceinline__ Tap2 ld_tap2(const float4* __restrict__ ra, const flo
   Tap2 t; t.a0 = ra[q]; t.a1 = ra[q + 1]; t.b0 = rb[q]; t.b1 = rb[q + 1]; return t;
 }
 
-template <bool kDoubleSums, bool kPrefetch, int MS_NT>
+// cv2.cartToPolar's magnitude: sqrt(fma(x, x, fl(y*y))) (bit-identical to cv2 4.13: oracle/farneback.py::cv_magnitude)
+__device__ __forceinline__ float magnitude(float dx, float dy) {
+  return __fsqrt_rn(__fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
+}
+
+// kMinMax: the launch that writes the final flow also reduces min / max of its magnitude per image into minmax[z][2]
+// (what flow_to_rgb's first normalisation needs): the colouring then skips its own pass over the flow.
+template <bool kDoubleSums, bool kPrefetch, int MS_NT, bool kMinMax = false>
 __global__ void __launch_bounds__(MS_NT, MS_NT == 256 ? 2 : 3)
 k4_flow_iter_march(const float4* __restrict__ RA0, const float* __restrict__ RB0, const float4* __restrict__ RA1,
                    const float* __restrict__ RB1, const float* __restrict__ flow_in, int h, int w, int rows_per_seg,
-                   float* __restrict__ flow_out) {
+                   float* __restrict__ flow_out, float* __restrict__ minmax = nullptr) {
   constexpr int MS_SX = MS_NT - 2 * MS_HALO;
+  float mag_mn = __int_as_float(0x7f800000), mag_mx = 0.f;
   extern __shared__ __align__(16) float ms_smem_buf[];
   float* ring = ms_smem_buf;                               // [15][5][MS_NT]
   float* hb = ms_smem_buf + 15 * 5 * MS_NT;                // [MS_RB][5][MS_NT] vertical sums of the current row batch
@@ -909,6 +917,10 @@ k4_flow_iter_march(const float4* __restrict__ RA0, const float* __restrict__ RB0
             const double idet = 1.0 / (g11 * g22 - g12 * g12 + 1e-3);
             f[o].x = (float)((g11 * h2 - g12 * h1) * idet);
             f[o].y = (float)((g22 * h1 - g12 * h2) * idet);
+            if (kMinMax && gx0 + o < w) {
+              const float m = magnitude(f[o].x, f[o].y);
+              mag_mn = fminf(mag_mn, m); mag_mx = fmaxf(mag_mx, m);
+            }
           }
           const size_t oi = zo + (size_t)gy * w + gx0;
           float2* dst = reinterpret_cast<float2*>(flow_out) + oi;
@@ -922,6 +934,16 @@ k4_flow_iter_march(const float4* __restrict__ RA0, const float* __restrict__ RB0
         }
       }
       __syncthreads();
+    }
+  }
+  if (kMinMax) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      mag_mn = fminf(mag_mn, __shfl_xor_sync(0xffffffffu, mag_mn, o)); mag_mx = fmaxf(mag_mx, __shfl_xor_sync(0xffffffffu, mag_mx, o));
+    }
+    if ((tx & 31) == 0) {                                   // magnitudes are >= 0: their bit patterns order like unsigned integers
+      atomicMin(reinterpret_cast<unsigned int*>(minmax + 2 * blockIdx.z), __float_as_uint(mag_mn));
+      atomicMax(reinterpret_cast<unsigned int*>(minmax + 2 * blockIdx.z + 1), __float_as_uint(mag_mx));
     }
   }
 }
@@ -1193,11 +1215,6 @@ k4_flow_upsample(const float* __restrict__ prev, int hp, int wp, int h, int w, d
 }
 
 // =========================================================================== flow colouring
-// cv2.cartToPolar's magnitude: sqrt(fma(x, x, fl(y*y))) (bit-identical to cv2 4.13: oracle/farneback.py::cv_magnitude)
-__device__ __forceinline__ float magnitude(float dx, float dy) {
-  return __fsqrt_rn(__fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
-}
-
 __global__ void k5_minmax_init(float* minmax, int B) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < B) { minmax[2 * i] = __int_as_float(0x7f800000); minmax[2 * i + 1] = 0.f; }
@@ -1493,6 +1510,7 @@ static int march_rows_per_seg(int h, int w, int sm_count, int MS_SX = 240, int p
 int flow_init_device_attrs() {
   VQA_CUDA(cudaFuncSetAttribute(k4_flow_iter, cudaFuncAttributeMaxDynamicSharedMemorySize, BX_SMEM));
   VQA_CUDA(cudaFuncSetAttribute(k4_flow_iter_march<true, true, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, ms_smem(256)));
+  VQA_CUDA(cudaFuncSetAttribute(k4_flow_iter_march<true, true, 256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ms_smem(256)));
   VQA_CUDA(cudaFuncSetAttribute(k4_flow_iter_march<false, true, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, ms_smem(256)));
   VQA_CUDA(cudaFuncSetAttribute(k4_flow_iter_march<true, true, 192>, cudaFuncAttributeMaxDynamicSharedMemorySize, ms_smem(192)));
   VQA_CUDA(cudaFuncSetAttribute(k4_flow_iter_march3<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, m2_smem()));
@@ -1508,11 +1526,15 @@ int flow_init_device_attrs() {
 
 using namespace b200vqa;
 
-extern "C" int b200vqa_farneback(b200vqa_t* h, const uint8_t* gray0, const uint8_t* gray1, int B, int H, int W, float* flow,
-                                 void* stream) {
-  if (!h || !gray0 || !gray1 || !flow || B <= 0 || H < 16 || W < 16) return B200VQA_EINVAL;
-  CtxScope scope(h);
-  cudaStream_t st = as_stream(stream);
+// minmax != nullptr: [B][2] min / max of the final flow's magnitude, reduced by the launch that writes the flow
+// (default streaming kernel only; otherwise a separate pass)
+static int farneback_impl(b200vqa_t* h, const uint8_t* gray0, const uint8_t* gray1, int B, int H, int W, float* flow, float* minmax,
+                          cudaStream_t st) {
+  if (minmax) {
+    k5_minmax_init<<<cdiv(B, 128), 128, 0, st>>>(minmax, B);
+    VQA_LAUNCH_CHECK();
+  }
+  bool minmax_done = false;
   const size_t P = (size_t)H * W;
   // workspace (float units): RA [2B][P] float4 | RB [2B][P] | I [2B][P/4] (levels >= 1 only) | flowA, flowB [B][P][2]
   const std::vector<Level> plan = pyramid_plan(H, W);
@@ -1628,7 +1650,11 @@ extern "C" int b200vqa_farneback(b200vqa_t* h, const uint8_t* gray0, const uint8
         else { VQA_CUDA(cudaEventCreate(&ev.first)); VQA_CUDA(cudaEventCreate(&ev.second)); }
         VQA_CUDA(cudaEventRecord(ev.first, st));
       }
-      if (h->flow_impl == 4) k4_flow_iter_march3<false><<<gmarch, M2_NT, m2_smem(), st>>>(RA0, RB0, RA1, RB1, fin, L.h, L.w, rows_per_seg, fout);
+      if (h->flow_impl == 0 && minmax && last && it == 2) {
+        k4_flow_iter_march<true, true, 256, true><<<gmarch, 256, ms_smem(256), st>>>(RA0, RB0, RA1, RB1, fin, L.h, L.w, rows_per_seg, fout, minmax);
+        minmax_done = true;
+      }
+      else if (h->flow_impl == 4) k4_flow_iter_march3<false><<<gmarch, M2_NT, m2_smem(), st>>>(RA0, RB0, RA1, RB1, fin, L.h, L.w, rows_per_seg, fout);
       else if (h->flow_impl == 5) k4_flow_iter_march3<true><<<gmarch, M2_NT, m2_smem(), st>>>(RA0, RB0, RA1, RB1, fin, L.h, L.w, rows_per_seg, fout);
       else if (h->flow_impl == 0) k4_flow_iter_march<true, true, 256><<<gmarch, 256, ms_smem(256), st>>>(RA0, RB0, RA1, RB1, fin, L.h, L.w, rows_per_seg, fout);
       else if (h->flow_impl == 3) k4_flow_iter_march<true, true, 192><<<gmarch, 192, ms_smem(192), st>>>(RA0, RB0, RA1, RB1, fin, L.h, L.w, rows_per_seg, fout);
@@ -1644,7 +1670,40 @@ extern "C" int b200vqa_farneback(b200vqa_t* h, const uint8_t* gray0, const uint8
     }
     prev = fout; ph = L.h; pw = L.w;
   }
+  if (minmax && !minmax_done) {
+    const size_t npix = (size_t)H * W;
+    int gx = (int)((npix + 256 * 8 - 1) / (256 * 8));
+    if (gx > 592) gx = 592;
+    k5_mag_minmax<<<dim3(gx, B), 256, 0, st>>>(flow, npix, minmax);
+    VQA_LAUNCH_CHECK();
+  }
   return B200VQA_OK;
+}
+
+static int launch_flow_rgb_sums(const float* flow, int B, int H, int W, const float* minmax, uint8_t* rgb, uint32_t* sums, cudaStream_t st) {
+  static const bool rgb_block = getenv("B200VQA_RGB_BLOCK") != nullptr;      // A/B: the 64 x 16 block form
+  // a band = one warp: short clips of small frames do not fill the GPU with bands (273 x 481 x 3: 216 warps), the block form does
+  const long bands = (long)B * cdiv(W, 128) * cdiv(H, 16);
+  if (rgb_block || bands < 2400) k5_flow_rgb_patchsum<<<dim3(cdiv(W, 64), cdiv(H, 16), B), dim3(64, 16), 0, st>>>(flow, H, W, minmax, rgb, sums);
+  else k5_flow_rgb_patchsum_band<<<dim3(cdiv(cdiv(W, 128), RG_WARPS), cdiv(H, 16), B), RG_WARPS * 32, 0, st>>>(flow, H, W, minmax, rgb, sums);
+  VQA_LAUNCH_CHECK();
+  return B200VQA_OK;
+}
+
+extern "C" int b200vqa_farneback(b200vqa_t* h, const uint8_t* gray0, const uint8_t* gray1, int B, int H, int W, float* flow,
+                                 void* stream) {
+  if (!h || !gray0 || !gray1 || !flow || B <= 0 || H < 16 || W < 16) return B200VQA_EINVAL;
+  CtxScope scope(h);
+  return farneback_impl(h, gray0, gray1, B, H, W, flow, nullptr, as_stream(stream));
+}
+
+extern "C" int b200vqa_farneback_flow_sums(b200vqa_t* h, const uint8_t* gray0, const uint8_t* gray1, int B, int H, int W, float* flow,
+                                           uint32_t* sums, float* minmax, void* stream) {
+  if (!h || !gray0 || !gray1 || !flow || !sums || !minmax || B <= 0 || H < 16 || W < 16) return B200VQA_EINVAL;
+  CtxScope scope(h);
+  cudaStream_t st = as_stream(stream);
+  int rc = farneback_impl(h, gray0, gray1, B, H, W, flow, minmax, st);
+  return rc ? rc : launch_flow_rgb_sums(flow, B, H, W, minmax, nullptr, sums, st);
 }
 
 extern "C" int b200vqa_flow_to_rgb(const float* flow, int B, int H, int W, uint8_t* rgb, uint32_t* sums, float* minmax,
@@ -1658,14 +1717,7 @@ extern "C" int b200vqa_flow_to_rgb(const float* flow, int B, int H, int W, uint8
   if (gx > 592) gx = 592;
   k5_mag_minmax<<<dim3(gx, B), 256, 0, st>>>(flow, npix, minmax);
   VQA_LAUNCH_CHECK();
-  if (rgb || sums) {
-    static const bool rgb_block = getenv("B200VQA_RGB_BLOCK") != nullptr;      // A/B: the 64 x 16 block form
-    // a band = one warp: short clips of small frames do not fill the GPU with bands (273 x 481 x 3: 216 warps), the block form does
-    const long bands = (long)B * cdiv(W, 128) * cdiv(H, 16);
-    if (rgb_block || bands < 2400) k5_flow_rgb_patchsum<<<dim3(cdiv(W, 64), cdiv(H, 16), B), dim3(64, 16), 0, st>>>(flow, H, W, minmax, rgb, sums);
-    else k5_flow_rgb_patchsum_band<<<dim3(cdiv(cdiv(W, 128), RG_WARPS), cdiv(H, 16), B), RG_WARPS * 32, 0, st>>>(flow, H, W, minmax, rgb, sums);
-    VQA_LAUNCH_CHECK();
-  }
+  if (rgb || sums) return launch_flow_rgb_sums(flow, B, H, W, minmax, rgb, sums, st);
   return B200VQA_OK;
 }
 

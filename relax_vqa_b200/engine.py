@@ -93,8 +93,7 @@ class Engine:
         r = ops.absdiff_patchsum(frames, nexts, want_residual=False, want_gray=True)
         pos, cnt = ops.topk_patches(r["sums"])
         ori, diff = ops.gather_fragments(frames, nexts, pos, cnt)
-        flow = ops.farneback(ctx, r["gray0"], r["gray1"])
-        _, fsums, minmax = ops.flow_to_rgb(flow, want_rgb=False, want_sums=True)
+        flow, fsums, minmax = ops.farneback_flow_sums(ctx, r["gray0"], r["gray1"])
         fpos, fcnt = ops.topk_patches(fsums)
         flow_frag, merged = ops.flow_fragment_merge(flow, minmax, fpos, fcnt, diff, want_flow_frag=keep_intermediates)
         if keep_intermediates:

@@ -172,6 +172,19 @@ def farneback(ctx, gray0, gray1):
     return flow
 
 
+def farneback_flow_sums(ctx, gray0, gray1):
+    """farneback + the colour statistics of flow_to_rgb in one call -> (flow [B,H,W,2], sums [B,gh,gw], minmax [B,2]);
+    the magnitude extrema come from the launch that writes the flow.  Bit-identical to farneback(); flow_to_rgb(want_rgb=False)."""
+    B, H, W = _u8(gray0).shape
+    dev = gray0.device
+    flow = torch.empty((B, H, W, 2), dtype=torch.float32, device=dev)
+    sums = torch.empty((B, H // PATCH, W // PATCH), dtype=torch.int32, device=dev)
+    minmax = torch.empty((B, 2), dtype=torch.float32, device=dev)
+    check(ctx.lib.b200vqa_farneback_flow_sums(ctx.h, ptr(gray0), ptr(_u8(gray1)), B, H, W, ptr(flow), ptr(sums), ptr(minmax),
+                                              stream_ptr(dev)), "farneback_flow_sums")
+    return flow, sums, minmax
+
+
 def flow_to_rgb(flow, want_rgb=True, want_sums=True):
     """flow [B,H,W,2] -> (rgb [B,H,W,3] u8 BGR or None, sums [B,gh,gw] or None, minmax [B,2])."""
     lib = _lib.load()

@@ -121,3 +121,24 @@ def test_reference_generated_flow_fixture(golden_dir):
         assert np.array_equal(frag[0].cpu().numpy(), g[f"flow_frag{t}"])
         merged = ops.merge_fragments(_dev(g[f"diff_frag{t}"]), frag[0])
         assert np.array_equal(merged.cpu().numpy(), g[f"merged{t}"])
+
+
+@pytest.mark.parametrize("impl", [0, 1])
+@pytest.mark.parametrize("hw", [(272, 480), (135, 241), (540, 960), (96, 500)])
+def test_farneback_flow_sums_equals_two_calls(ctx, hw, impl):
+    """The engine's fused call (magnitude extrema reduced by the launch that writes the final flow, then the colour patch
+    sums) against farneback() followed by flow_to_rgb(): flow, extrema and sums bit for bit."""
+    from relax_vqa_b200 import ops, synth
+    fr, nx = synth.make_clip(11, hw[0], hw[1], 3)
+    g0 = _dev(np.stack([F.bgr2gray(f) for f in fr]))
+    g1 = _dev(np.stack([F.bgr2gray(f) for f in nx]))
+    ctx.set_flow_impl(impl)
+    try:
+        flow, sums, mm = ops.farneback_flow_sums(ctx, g0, g1)
+        ref = ops.farneback(ctx, g0, g1)
+    finally:
+        ctx.set_flow_impl(0)
+    _, rsums, rmm = ops.flow_to_rgb(ref, want_rgb=False)
+    assert torch.equal(flow, ref)
+    assert torch.equal(mm, rmm)
+    assert torch.equal(sums, rsums)

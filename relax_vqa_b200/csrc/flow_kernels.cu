@@ -440,17 +440,21 @@ k4_polyexp_march(const float* __restrict__ I, const uint8_t* __restrict__ gray0,
     img = I + (size_t)z * h * w + cx;
   }
   auto hrow = [&](int r) -> int { const int o = r * w; return (int)gl[o] + 2 * (int)gc[o] + (int)gr[o]; };
+  // look-ahead rows are kept as the three raw bytes: summing them where they are loaded made every load wait for itself
+  // (ncu: 34 % of the stall samples on that line); they are summed one iteration later, BEFORE the next loads are issued
+  // (ptxas tracks all global loads of the kernel on one scoreboard, so a consumer placed after newer loads waits for those too)
+  auto hraw = [&](int r, uint8_t (&b)[3]) { const int o = r * w; b[0] = gl[o]; b[1] = gc[o]; b[2] = gr[o]; };
   auto crow = [&](int k) -> int { return min(max(ya - PE_N + k, 0), h - 1); };        // image row of march step k
   float win[11];
 #pragma unroll
   for (int i = 0; i < 11; ++i) win[i] = 0.f;
   int ha = 0, hb = 0, hc = 0, prev_cy = crow(0);
-  int hn[4] = {0, 0, 0, 0};                        // inputs of march steps k .. k + 3 (two iterations of look-ahead)
+  uint8_t hraw2[2][3] = {{0, 0, 0}, {0, 0, 0}};   // raw inputs of march steps k, k + 1 (loaded one iteration ahead)
   float fn[4] = {0.f, 0.f, 0.f, 0.f};
   if (kFromGray) {
     ha = hrow(reflect101(prev_cy - 1, h)); hb = hrow(prev_cy); hc = hrow(reflect101(prev_cy + 1, h));
 #pragma unroll
-    for (int u = 0; u < 4; ++u) hn[u] = hrow(reflect101(crow(u) + 1, h));
+    for (int u = 0; u < 2; ++u) hraw(reflect101(crow(u) + 1, h), hraw2[u]);
   } else {
 #pragma unroll
     for (int u = 0; u < 4; ++u) fn[u] = img[(size_t)crow(u) * w];
@@ -458,11 +462,12 @@ k4_polyexp_march(const float* __restrict__ I, const uint8_t* __restrict__ gray0,
   const int nk = 10 + ((yb - ya + PM_RB - 1) & ~(PM_RB - 1));
   for (int k = 0; k < nk; k += 2) {
     float in2[2];
-    int hcur[2] = {hn[0], hn[1]};
+    int hcur[2] = {0, 0};
     if (kFromGray) {
-      hn[0] = hn[2]; hn[1] = hn[3];
 #pragma unroll
-      for (int u = 0; u < 2; ++u) hn[2 + u] = hrow(reflect101(crow(k + 4 + u) + 1, h));
+      for (int u = 0; u < 2; ++u) hcur[u] = (int)hraw2[u][0] + 2 * (int)hraw2[u][1] + (int)hraw2[u][2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) hraw(reflect101(crow(k + 2 + u) + 1, h), hraw2[u]);
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
         const int cy = crow(k + u);
@@ -1682,9 +1687,10 @@ static int farneback_impl(b200vqa_t* h, const uint8_t* gray0, const uint8_t* gra
 
 static int launch_flow_rgb_sums(const float* flow, int B, int H, int W, const float* minmax, uint8_t* rgb, uint32_t* sums, cudaStream_t st) {
   static const bool rgb_block = getenv("B200VQA_RGB_BLOCK") != nullptr;      // A/B: the 64 x 16 block form
+  static const bool rgb_band = getenv("B200VQA_RGB_BAND") != nullptr;        // force the band form on small batches (sanitizer pass)
   // a band = one warp: short clips of small frames do not fill the GPU with bands (273 x 481 x 3: 216 warps), the block form does
   const long bands = (long)B * cdiv(W, 128) * cdiv(H, 16);
-  if (rgb_block || bands < 2400) k5_flow_rgb_patchsum<<<dim3(cdiv(W, 64), cdiv(H, 16), B), dim3(64, 16), 0, st>>>(flow, H, W, minmax, rgb, sums);
+  if (rgb_block || (bands < 2400 && !rgb_band)) k5_flow_rgb_patchsum<<<dim3(cdiv(W, 64), cdiv(H, 16), B), dim3(64, 16), 0, st>>>(flow, H, W, minmax, rgb, sums);
   else k5_flow_rgb_patchsum_band<<<dim3(cdiv(cdiv(W, 128), RG_WARPS), cdiv(H, 16), B), RG_WARPS * 32, 0, st>>>(flow, H, W, minmax, rgb, sums);
   VQA_LAUNCH_CHECK();
   return B200VQA_OK;

@@ -1,6 +1,8 @@
 """Tiny end-to-end pass for compute-sanitizer (memcheck / racecheck): every kernel once, small shapes - the inference path
 (two resolutions), the raw-map / token boundary path, the yuv sampler and two trainer steps."""
 import os, sys
+os.environ.setdefault("B200VQA_PYR_OS3", "8")      # small frames still go through the fused pyramid kernel
+os.environ.setdefault("B200VQA_RGB_BAND", "1")     # ... and the warp-per-band colouring kernel
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from relax_vqa_b200 import ops, synth, weights
@@ -13,6 +15,12 @@ for hw in ((144, 256), (100, 150)):
     feats, score = eng.predict([Clip(torch.from_numpy(fr).cuda(), torch.from_numpy(nx).cuda())], "konvid_1k")
     torch.cuda.synchronize()
     print(hw, float(score[0]), bool(torch.isfinite(feats).all()))
+g0 = torch.randint(0, 256, (2, 272, 480), dtype=torch.uint8, device="cuda")
+flow, fsums, mm = ops.farneback_flow_sums(eng.ctx, g0, torch.roll(g0, 2, 2))
+A = (torch.randn(300, 128, device="cuda") * 0.5).half(); Bm = (torch.randn(256, 128, device="cuda") * 0.5).half()
+d4 = ops.gemm_f16(eng.ctx, A, Bm, None, impl=3)
+torch.cuda.synchronize()
+print("flow_sums", tuple(flow.shape), int(fsums.sum()), "gemm4cta", bool(torch.isfinite(d4).all()))
 img = torch.randint(0, 256, (2, 224, 224, 3), dtype=torch.uint8, device="cuda")
 maps = ops.resnet50_maps(eng.ctx, img)
 tok = ops.vitb16_tokens(eng.ctx, img)

@@ -1574,8 +1574,18 @@ static int farneback_impl(b200vqa_t* h, const uint8_t* gray0, const uint8_t* gra
     }
     // too few threads for a streaming kernel (short clips of small frames): the tile kernel is as fast there
     const int G = W >> 3, p3 = (H + 7) >> 3;
+    // segment height (in level-3 rows = 8 source rows; each segment re-reads 16 rows of window overlap): whole waves of the
+    // 4 x SM-count resident blocks at the least rows per block.  Every output row is computed inside one segment, so the
+    // split changes no result bit.
     int os3 = 0;
-    for (int cand : {15, 8, 4}) if (!os3 && (long)2 * B * G * cdiv(p3, cand) >= 40000) os3 = cand;
+    if ((long)2 * B * G * cdiv(p3, 4) >= 40000) {
+      const long resident = 4L * h->sm_count, per_seg = (long)cdiv(G, PF_NT) * 2 * B;
+      long best = -1;
+      for (int cand = 4; cand <= p3; ++cand) {
+        const long blocks = per_seg * cdiv(p3, cand), waves = (blocks + resident - 1) / resident, cost = waves * (cand + 2);
+        if (best < 0 || cost < best) { best = cost; os3 = cand; }
+      }
+    }
     if (const char* e = getenv("B200VQA_PYR_OS3")) os3 = atoi(e);
     if (!os3) fused[1] = fused[2] = fused[3] = false;
     const int mask = (fused[1] ? 1 : 0) | (fused[2] ? 2 : 0) | (fused[3] ? 4 : 0);

@@ -746,18 +746,47 @@ __device__ __forceinline__ float magnitude(float dx, float dy) {
   return __fsqrt_rn(__fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
 }
 
+// cv::resize(prev, (w, h), INTER_LINEAR) * 2 between pyramid levels: source cell and weight of one output coordinate (computed
+// in double, as OpenCV does) and the bilinear combination, in the association k4_flow_upsample has always compiled to.
+struct UpCoord { int i0, i1; float a; };
+__device__ __forceinline__ UpCoord up_coord(int o, double scale, int n_in) {
+  const double s = (o + 0.5) * scale - 0.5;
+  int f = (int)floor(s);
+  UpCoord c; c.a = (float)(s - f);
+  if (f < 0) { f = 0; c.a = 0.f; }
+  c.i0 = f; c.i1 = f + 1;
+  if (f >= n_in - 1) { c.i0 = c.i1 = n_in - 1; c.a = 0.f; }
+  return c;
+}
+__device__ __forceinline__ float up_mix(float p00, float p01, float p10, float p11, float ax, float ay) {
+  const float omx = __fsub_rn(1.f, ax);
+  const float h0 = __fmaf_rn(p00, omx, __fmul_rn(p01, ax)), h1 = __fmaf_rn(p10, omx, __fmul_rn(p11, ax));
+  const float v = __fmaf_rn(h0, __fsub_rn(1.f, ay), __fmul_rn(ay, h1));
+  return __fadd_rn(v, v);
+}
+__device__ __forceinline__ float2 up_sample(const float2* __restrict__ p, int wp, const UpCoord& cy, const UpCoord& cx) {
+  const float2 p00 = p[(size_t)cy.i0 * wp + cx.i0], p01 = p[(size_t)cy.i0 * wp + cx.i1];
+  const float2 p10 = p[(size_t)cy.i1 * wp + cx.i0], p11 = p[(size_t)cy.i1 * wp + cx.i1];
+  return make_float2(up_mix(p00.x, p01.x, p10.x, p11.x, cx.a, cy.a), up_mix(p00.y, p01.y, p10.y, p11.y, cx.a, cy.a));
+}
+struct UpSrc { const float* prev; int hp, wp; double sx, sy; };     // the coarser level's flow (kUp)
+
 // kMinMax: the launch that writes the final flow also reduces min / max of its magnitude per image into minmax[z][2]
 // (what flow_to_rgb's first normalisation needs): the colouring then skips its own pass over the flow.
-template <bool kDoubleSums, bool kPrefetch, int MS_NT, bool kMinMax = false>
+// kUp: the first iteration of a level reads its input flow straight from the coarser level (the bilinear x 2 upsample of
+// k4_flow_upsample evaluated where the flow is consumed: the level's upsampled field is never written to or read from HBM);
+// the rows' source coordinates sit in a shared-memory table built once per block, the column's in registers.
+template <bool kDoubleSums, bool kPrefetch, int MS_NT, bool kMinMax = false, bool kUp = false>
 __global__ void __launch_bounds__(MS_NT, MS_NT == 256 ? 2 : 3)
 k4_flow_iter_march(const float4* __restrict__ RA0, const float* __restrict__ RB0, const float4* __restrict__ RA1,
                    const float* __restrict__ RB1, const float* __restrict__ flow_in, int h, int w, int rows_per_seg,
-                   float* __restrict__ flow_out, float* __restrict__ minmax = nullptr) {
+                   float* __restrict__ flow_out, float* __restrict__ minmax = nullptr, UpSrc up = UpSrc{}) {
   constexpr int MS_SX = MS_NT - 2 * MS_HALO;
   float mag_mn = __int_as_float(0x7f800000), mag_mx = 0.f;
   extern __shared__ __align__(16) float ms_smem_buf[];
   float* ring = ms_smem_buf;                               // [15][5][MS_NT]
   float* hb = ms_smem_buf + 15 * 5 * MS_NT;                // [MS_RB][5][MS_NT] vertical sums of the current row batch
+  UpCoord* uprow = reinterpret_cast<UpCoord*>(hb + MS_RB * 5 * MS_NT);      // kUp: [nk + 4] source rows of march steps 0 ..
   const int tx = threadIdx.x;
   const int x0 = blockIdx.x * MS_SX;
   const int ya = blockIdx.y * rows_per_seg, yb = min(ya + rows_per_seg, h);
@@ -781,11 +810,24 @@ k4_flow_iter_march(const float4* __restrict__ RA0, const float* __restrict__ RB0
   // flow vectors head the dependent chain flow -> tap address -> taps: they are fetched two iterations ahead, and one
   // iteration ahead their tap lines (and the R0 lines) are requested into L2, so the demand loads of an iteration find
   // an L2 hit instead of a DRAM access (kPrefetch)
+  UpCoord upx{0, 0, 0.f};
+  const float2* upp = nullptr;
+  if (kUp) {
+    for (int i = tx; i < nk + 4; i += MS_NT) uprow[i] = up_coord(min(max(ya - 7 + i, 0), h - 1), up.sy, up.hp);
+    upx = up_coord(x, up.sx, up.wp);
+    upp = reinterpret_cast<const float2*>(up.prev) + (size_t)blockIdx.z * up.hp * up.wp;
+    __syncthreads();
+  }
+  // input flow of march step kidx (row clamp(ya - 7 + kidx)) at this thread's column
+  auto flow_at = [&](int kidx) -> float2 {
+    if (kUp) return up_sample(upp, up.wp, uprow[kidx], upx);
+    return fin[min(max(ya - 7 + kidx, 0), h - 1) * w + x];
+  };
   float2 dn[2], dnn[2];
 #pragma unroll
   for (int u = 0; u < 2; ++u) {
-    dn[u] = fin[min(max(ya - 7 + u, 0), h - 1) * w + x];
-    dnn[u] = fin[min(max(ya - 7 + 2 + u, 0), h - 1) * w + x];
+    dn[u] = flow_at(u);
+    dnn[u] = flow_at(2 + u);
   }
   Tap2 pbot; pbot.a0 = pbot.a1 = make_float4(0.f, 0.f, 0.f, 0.f); pbot.b0 = pbot.b1 = 0.f;
   int pq = -1;                                                              // address of the row held in pbot
@@ -818,7 +860,7 @@ k4_flow_iter_march(const float4* __restrict__ RA0, const float* __restrict__ RB0
     for (int u = 0; u < 2; ++u) {
       dn[u] = dnn[u];
       const int yn = min(max(ya - 7 + k + 2 + u, 0), h - 1);
-      dnn[u] = fin[min(max(ya - 7 + k + 4 + u, 0), h - 1) * w + x];
+      dnn[u] = flow_at(k + 4 + u);
       if (kPrefetch) {
         const int on = yn * w + x;
         const int x1 = (int)floorf((float)x + dn[u].x), y1 = (int)floorf((float)yn + dn[u].y);
@@ -1189,33 +1231,17 @@ k4_flow_iter_march3(const float4* __restrict__ RA0, const float* __restrict__ RB
 constexpr int UP_ROWS = 8;
 __global__ void __launch_bounds__(256)
 k4_flow_upsample(const float* __restrict__ prev, int hp, int wp, int h, int w, double sx, double sy, float* __restrict__ out) {
-  __shared__ int s_y0[UP_ROWS], s_y1[UP_ROWS];
-  __shared__ float s_ay[UP_ROWS];
+  __shared__ UpCoord s_y[UP_ROWS];
   const int xo = blockIdx.x * blockDim.x + threadIdx.x, yb = blockIdx.y * UP_ROWS;
-  if (threadIdx.x < UP_ROWS) {
-    const double s = (yb + threadIdx.x + 0.5) * sy - 0.5; int f = (int)floor(s); float ay = (float)(s - f);
-    int y0, y1;
-    if (f < 0) { f = 0; ay = 0.f; } y0 = f; y1 = f + 1; if (f >= hp - 1) { y0 = y1 = hp - 1; ay = 0.f; }
-    s_y0[threadIdx.x] = y0; s_y1[threadIdx.x] = y1; s_ay[threadIdx.x] = ay;
-  }
+  if (threadIdx.x < UP_ROWS) s_y[threadIdx.x] = up_coord(yb + threadIdx.x, sy, hp);
   __syncthreads();
   if (xo >= w) return;
   const float2* p = reinterpret_cast<const float2*>(prev) + (size_t)blockIdx.z * hp * wp;
-  const double s = (xo + 0.5) * sx - 0.5; int f = (int)floor(s); float ax = (float)(s - f);
-  int x0, x1;
-  if (f < 0) { f = 0; ax = 0.f; } x0 = f; x1 = f + 1; if (f >= wp - 1) { x0 = x1 = wp - 1; ax = 0.f; }
+  const UpCoord cx = up_coord(xo, sx, wp);
   float2* o = reinterpret_cast<float2*>(out) + ((size_t)blockIdx.z * h + yb) * w + xo;
 #pragma unroll
   for (int r = 0; r < UP_ROWS; ++r) {
-    if (yb + r < h) {
-      const int y0 = s_y0[r], y1 = s_y1[r];
-      const float ay = s_ay[r];
-      const float2 p00 = p[(size_t)y0 * wp + x0], p01 = p[(size_t)y0 * wp + x1], p10 = p[(size_t)y1 * wp + x0], p11 = p[(size_t)y1 * wp + x1];
-      float2 v;
-      v.x = ((p00.x * (1.f - ax) + p01.x * ax) * (1.f - ay) + (p10.x * (1.f - ax) + p11.x * ax) * ay) * 2.f;
-      v.y = ((p00.y * (1.f - ax) + p01.y * ax) * (1.f - ay) + (p10.y * (1.f - ax) + p11.y * ax) * ay) * 2.f;
-      o[(size_t)r * w] = v;
-    }
+    if (yb + r < h) o[(size_t)r * w] = up_sample(p, wp, s_y[r], cx);
   }
 }
 
@@ -1516,6 +1542,7 @@ int flow_init_device_attrs() {
   VQA_CUDA(cudaFuncSetAttribute(k4_flow_iter, cudaFuncAttributeMaxDynamicSharedMemorySize, BX_SMEM));
   VQA_CUDA(cudaFuncSetAttribute(k4_flow_iter_march<true, true, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, ms_smem(256)));
   VQA_CUDA(cudaFuncSetAttribute(k4_flow_iter_march<true, true, 256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ms_smem(256)));
+  VQA_CUDA(cudaFuncSetAttribute(k4_flow_iter_march<true, true, 256, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ms_smem(256) + 16 * 1024));
   VQA_CUDA(cudaFuncSetAttribute(k4_flow_iter_march<false, true, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, ms_smem(256)));
   VQA_CUDA(cudaFuncSetAttribute(k4_flow_iter_march<true, true, 192>, cudaFuncAttributeMaxDynamicSharedMemorySize, ms_smem(192)));
   VQA_CUDA(cudaFuncSetAttribute(k4_flow_iter_march3<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, m2_smem()));
@@ -1647,15 +1674,25 @@ static int farneback_impl(b200vqa_t* h, const uint8_t* gray0, const uint8_t* gra
     if (!prev) {
       VQA_CUDA(cudaMemsetAsync(fin, 0, (size_t)B * lp * 2 * sizeof(float), st));
       count_launch();
-    } else {
-      fin = (prev == flowA) ? flowB : flowA;
-      k4_flow_upsample<<<dim3(cdiv(L.w, 256), cdiv(L.h, UP_ROWS), B), 256, 0, st>>>(prev, ph, pw, L.h, L.w, (double)pw / L.w, (double)ph / L.h, fin);
-      VQA_LAUNCH_CHECK();
     }
     const dim3 gbox(cdiv(L.w, BX_TX), cdiv(L.h, BX_TY), B);
     const int nt = h->flow_impl == 3 ? 192 : 256;
     const int rows_per_seg = march_rows_per_seg(L.h, L.w, 148, ms_sx(nt), nt == 256 ? 2 : 3);      // fixed SM count: the split must not vary between devices
     const dim3 gmarch(cdiv(L.w, ms_sx(nt)), cdiv(L.h, rows_per_seg), B);
+    // A/B (B200VQA_UPSAMPLE_FUSED): the first iteration upsamples the coarser level's flow where it reads it instead of a
+    // k4_flow_upsample pass.  Bit-identical; MEASURED 4.383 vs 4.417 ms per 22 pairs of 1080p, 5.632 vs 5.620 at 2160p x 6 -
+    // the four dependent loads at the head of the flow -> tap chain cost the iteration what the pass saved.  Off by default.
+    static const bool up_opt_in = getenv("B200VQA_UPSAMPLE_FUSED") != nullptr;
+    const size_t up_table = (((size_t)rows_per_seg + 24) * sizeof(UpCoord) + 15) & ~(size_t)15;      // must leave room for two blocks per SM
+    const bool up_fused = prev && h->flow_impl == 0 && up_opt_in && up_table <= 16 * 1024;
+    if (prev) {
+      if (up_fused) fin = prev;        // read through UpSrc; the first iteration writes the other buffer
+      else {
+        fin = (prev == flowA) ? flowB : flowA;
+        k4_flow_upsample<<<dim3(cdiv(L.w, 256), cdiv(L.h, UP_ROWS), B), 256, 0, st>>>(prev, ph, pw, L.h, L.w, (double)pw / L.w, (double)ph / L.h, fin);
+        VQA_LAUNCH_CHECK();
+      }
+    }
     float* fout = nullptr;
     for (int it = 0; it < 3; ++it) {
       fout = (last && it == 2) ? flow : (fin == flowA ? flowB : flowA);
@@ -1665,7 +1702,11 @@ static int farneback_impl(b200vqa_t* h, const uint8_t* gray0, const uint8_t* gra
         else { VQA_CUDA(cudaEventCreate(&ev.first)); VQA_CUDA(cudaEventCreate(&ev.second)); }
         VQA_CUDA(cudaEventRecord(ev.first, st));
       }
-      if (h->flow_impl == 0 && minmax && last && it == 2) {
+      if (up_fused && it == 0) {
+        const UpSrc up{prev, ph, pw, (double)pw / L.w, (double)ph / L.h};
+        k4_flow_iter_march<true, true, 256, false, true><<<gmarch, 256, ms_smem(256) + up_table, st>>>(RA0, RB0, RA1, RB1, nullptr, L.h, L.w, rows_per_seg, fout, nullptr, up);
+      }
+      else if (h->flow_impl == 0 && minmax && last && it == 2) {
         k4_flow_iter_march<true, true, 256, true><<<gmarch, 256, ms_smem(256), st>>>(RA0, RB0, RA1, RB1, fin, L.h, L.w, rows_per_seg, fout, minmax);
         minmax_done = true;
       }

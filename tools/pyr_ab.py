@@ -1,6 +1,8 @@
-"""A/B of the pyramid kernels: fused streaming kernel (default) vs the per-level tile kernel (B200VQA_PYR_TILE=1).
-Each variant runs in its own process (the switch is read once); flows are compared and the whole farneback call is timed.
-python tools/pyr_ab.py [--height 1080 --width 1920 --pairs 22]"""
+"""A/B of the Farneback path against its environment switches, each variant in its own process (the switches are read
+once): default vs B200VQA_PYR_TILE (per-level tile pyramid kernel instead of the fused streaming one), B200VQA_UPSAMPLE_FUSED
+(upsampling inside the first iteration of a level instead of the separate flow-upsample pass), ...  Flows are compared bit for bit and the
+whole farneback call is timed.
+python tools/pyr_ab.py [--height 1080 --width 1920 --pairs 22 --envs B200VQA_PYR_TILE,B200VQA_UPSAMPLE_FUSED]"""
 import argparse
 import os
 import subprocess
@@ -13,6 +15,7 @@ ap.add_argument("--height", type=int, default=1080)
 ap.add_argument("--width", type=int, default=1920)
 ap.add_argument("--pairs", type=int, default=22)
 ap.add_argument("--child", default="")
+ap.add_argument("--envs", default="B200VQA_PYR_TILE,B200VQA_UPSAMPLE_FUSED")
 args = ap.parse_args()
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if args.child:
@@ -37,13 +40,15 @@ if args.child:
     np.save(args.child, flow.cpu().numpy())
     ctx.close()
     sys.exit(0)
-outs = []
-for name, env in (("fused", {}), ("tile", {"B200VQA_PYR_TILE": "1"}), ("split", {"B200VQA_PYR_SPLIT": "1"})):
+outs = {}
+variants = [("default", {})] + [(e, {e: "1"}) for e in args.envs.split(",") if e]
+for name, env in variants:
     path = f"/tmp/pyr_ab_{name}.npy"
     e = dict(os.environ); e.update(env)
     r = subprocess.run([sys.executable, __file__, "--child", path, "--height", str(args.height), "--width", str(args.width),
                         "--pairs", str(args.pairs)], env=e, capture_output=True, text=True)
     print(r.stdout.strip() or r.stderr[-400:])
-    outs.append(np.load(path))
-d = np.abs(outs[0] - outs[1])
-print(f"{args.height}x{args.width}: max |flow_fused - flow_tile| = {d.max():.3e} px, mean {d.mean():.3e} px; split identical: {bool(np.array_equal(outs[0], outs[2]))}")
+    outs[name] = np.load(path)
+for name, _ in variants[1:]:
+    d = np.abs(outs["default"] - outs[name])
+    print(f"{args.height}x{args.width}: max |flow_default - flow[{name}]| = {d.max():.3e} px, mean {d.mean():.3e} px")

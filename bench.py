@@ -367,6 +367,21 @@ def main():
         eng.predict(clips, video_type)
     gemm_ms, gemm_launches, gemm_flops = eng.ctx.profile_read()
     flow_ms, flow_launches, flow_bytes = eng.profile_read_flow()
+    # the same per-launch timing split by kernel: the ViT linears (SM-pair kernel) and the ResNet convolutions (implicit GEMM,
+    # HBM-bound on the 56x56 / 28x28 layers) on a batch of one step's backbone images
+    from relax_vqa_b200 import ops as _ops
+    n_img = max(1, min(3 * my_pairs, 512))
+    probe = torch.randint(0, 256, (n_img, 224, 224, 3), dtype=torch.uint8, device=eng.device)
+    by_kernel = {}
+    for name, fn in (("gemm_tcgen05_kernel (ResNet-50 convolutions)", lambda: _ops.resnet50_features(eng.ctx, probe, is_bgr=True, want_stack=True, want_pool=True)),
+                     ("gemm2cta_tcgen05_kernel (ViT-B/16 linears)", lambda: _ops.vitb16_features(eng.ctx, probe, is_bgr=True))):
+        fn()
+        eng.ctx.profile_read()
+        fn()
+        k_ms, k_n, k_fl = eng.ctx.profile_read()
+        k_tf = k_fl / (k_ms / 1e3) / 1e12 if k_ms > 0 else 0.0
+        by_kernel[name] = dict(achieved=k_tf, frac=k_tf / peaks["tf_sustained"], launches=k_n, ms=k_ms, images=n_img)
+    del probe
     eng.set_profiling(False)
     eng.concurrent = True
     step_ms = ms / args.steps
@@ -378,7 +393,7 @@ def main():
     roofline = dict(bound="tensor", kernel="gemm_tcgen05_kernel", achieved=achieved, peak=peaks["tf_sustained"], unit="TFLOP/s",
                     frac=achieved / peaks["tf_sustained"], traffic=traffic, peak_source=peaks["src"] + " (sustained fp16/bf16 dense)",
                     launches_per_step=gemm_launches // 2, kernel_ms_per_step=gemm_ms / 2, share_of_step=(gemm_ms / 2) / step_ms,
-                    algorithmic_gflop_per_pair=gemm_flops / 2 / max(my_pairs, 1) / 1e9)
+                    algorithmic_gflop_per_pair=gemm_flops / 2 / max(my_pairs, 1) / 1e9, by_kernel=by_kernel)
     flow_gbs = flow_bytes / (flow_ms / 1e3) / 1e9 if flow_ms > 0 else 0.0
     ratio, fsrc = 1.0, None
     fp = os.path.join(ROOT, "profiles", "flow_traffic.json")

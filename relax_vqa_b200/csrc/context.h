@@ -33,6 +33,7 @@ struct b200vqa_ctx {
   int device = 0;
   int sm_count = 148;
   int gemm_sms = 0;                        // > 0: persistent tcgen05 grids use this many SMs (b200vqa_set_gemm_sms)
+  int conv_no_halo = 0;                    // set while the raw-map boundary path runs (generic per-tap convolutions there)
   int gemm_impl = 0;                       // 0 tcgen05, 1 SIMT check kernels
   int attn_impl = 0;                       // 0 tcgen05 / TMEM attention, 1 warp-level mma.sync attention (A/B)
   int flow_impl = 0;                       // 0 streaming strip kernels (f64 running sums), 1 same with Kahan fp32 sums, 2 tile kernels,

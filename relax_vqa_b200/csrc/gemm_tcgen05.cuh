@@ -71,6 +71,14 @@ struct GemmParams {
   float* gap_partial;            // EPI_CONV: [Nimg][tiles_y * GEMM_EPI_GROUPS][Cout] or null
   int gap_raw;                   // pool the raw accumulator (conv1 hook is pre-BN)
   int dbg_skip_epilogue;         // profiling experiments only (B200VQA_GEMM_NOEPI=1): drain nothing, store nothing
+  // halo mode (3x3, stride 1, pad 1): the activation tile is fetched ONCE per channel block with its one-pixel halo and the nine
+  // taps read it as shifted views (a K-major SWIZZLE_128B operand may start at any 128-byte row: tools/probes/desc_probe.py);
+  // block_n = th * halo_pitch rounded up to 16 accumulator columns, column y * halo_pitch + x = output pixel (y, x)
+  int halo;                      // 0 / 1
+  int halo_pitch;                // pixels per haloed row (Wout + 2)
+  int halo_rows_img;             // (th + 2) * halo_pitch: haloed pixels per image of the tile
+  int halo_bytes;                // one halo buffer (box + over-read padding, multiple of 1024)
+  int dbg_bshift, dbg_bbase;     // descriptor probe (tools/probes/desc_probe.py): B operand read from row dbg_bshift of the tile, base-offset field dbg_bbase
 };
 
 // ------------------------------------------------------------------------------ PTX helpers
@@ -338,12 +346,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const uint32_t a_bytes = GEMM_BM * GEMM_BK * 2;
   const uint32_t b_bytes = (uint32_t)p.block_n * GEMM_BK * 2;
-  const uint32_t stage_bytes = a_bytes + b_bytes;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
+  const uint32_t stage_bytes = p.halo ? a_bytes : a_bytes + b_bytes;       // halo mode: the ring holds weight K-blocks only
+  uint8_t* halo_buf = smem + (size_t)p.stages * stage_bytes;               // halo mode: two haloed activation tiles
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(halo_buf + (p.halo ? 2 * (size_t)p.halo_bytes : 0));
   uint64_t* empty_bar = full_bar + GEMM_MAX_STAGES;
   uint64_t* tmem_full = empty_bar + GEMM_MAX_STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* halo_full = tmem_empty + 2;
+  uint64_t* halo_empty = halo_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(halo_empty + 2);
   float* epi_stage = reinterpret_cast<float*>(tmem_slot + 4);        // [GEMM_EPI_WARPS][32][EPI_LD] fp32, 16-byte aligned
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -357,7 +368,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < p.stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], GEMM_EPI_WARPS); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], GEMM_EPI_WARPS); mbar_init(&halo_full[i], 1); mbar_init(&halo_empty[i], 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -373,6 +384,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     // ================================ TMA producer ================================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
+      int hb = 0; uint32_t hphase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int mt = tile % p.m_tiles, nt = tile / p.m_tiles;
         int bx = 0, by = 0, bn = 0;
@@ -381,6 +393,22 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
           by = ty * p.th * p.conv_stride - p.conv_pad;
           bx = -p.conv_pad;
           bn = tg * p.tn;
+        }
+        if (p.halo) {
+          const uint32_t box_bytes = (uint32_t)p.halo_rows_img * (uint32_t)p.tn * 128u;
+          for (int cb = 0; cb < p.k_blocks_per_tap; ++cb) {
+            mbar_wait(&halo_empty[hb], hphase ^ 1);
+            mbar_expect_tx(&halo_full[hb], box_bytes);
+            tma_load_4d(&map_b, &halo_full[hb], halo_buf + (size_t)hb * p.halo_bytes, cb * GEMM_BK, bx, by, bn);
+            for (int tap = 0; tap < 9; ++tap) {
+              mbar_wait(&empty_bar[stage], phase ^ 1);
+              mbar_expect_tx(&full_bar[stage], a_bytes);
+              tma_load_2d(&map_a, &full_bar[stage], smem + (size_t)stage * stage_bytes, (tap * p.k_blocks_per_tap + cb) * GEMM_BK, mt * GEMM_BM);
+              if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            }
+            if (++hb == 2) { hb = 0; hphase ^= 1; }
+          }
+          continue;
         }
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -416,18 +444,56 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     // ================================ MMA issuer ==================================
     const uint32_t idesc = make_idesc(p.block_n);
     int stage = 0; uint32_t phase = 0;
+    int hb = 0; uint32_t hphase = 0;
     int acc = 0; uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       if (lane == 0) mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
       __syncwarp();
       tcgen05_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)acc * 256u;
+      if (p.halo) {
+        // One MMA per tap and K step, as in the per-tap-box path: for tap (r, s) the th output rows of the tile are th * pitch
+        // CONSECUTIVE rows of the haloed tile starting at row r * pitch + s (the two halo columns between image rows become two
+        // masked accumulator columns per row).  N = block_n = th * pitch rounded up to 16.  (Per-row MMAs of N = 64 / 32 / 16 were
+        // 2-6x slower: a tcgen05.mma costs ~120 clk whatever its N.)
+        if (lane == 0) {
+          for (int cb = 0; cb < p.k_blocks_per_tap; ++cb) {
+            mbar_wait(&halo_full[hb], hphase);
+            const uint64_t hdesc = make_smem_desc(smem_u32(halo_buf + (size_t)hb * p.halo_bytes));
+            for (int tap = 0; tap < 9; ++tap) {
+              const int r = tap / 3, sft = tap - 3 * r;
+              mbar_wait(&full_bar[stage], phase);
+              tcgen05_fence_after();
+              const uint64_t adesc = make_smem_desc(smem_u32(smem + (size_t)stage * stage_bytes));
+              const uint64_t bdesc = hdesc + (uint64_t)((r * p.halo_pitch + sft) * 8);      // 128-byte rows = 8 descriptor units
+#pragma unroll
+              for (int k = 0; k < GEMM_BK / 16; ++k)
+                tcgen05_mma_f16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (cb | tap | k) != 0);
+              tcgen05_commit(&empty_bar[stage]);
+              if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            }
+            tcgen05_commit(&halo_empty[hb]);            // the haloed tile may be overwritten when these MMAs retire
+            if (++hb == 2) { hb = 0; hphase ^= 1; }
+          }
+          tcgen05_commit(&tmem_full[acc]);
+        }
+        __syncwarp();
+        // every lane tracks the ring positions
+        if (lane != 0) {
+          const int adv = 9 * p.k_blocks_per_tap;
+          for (int i = 0; i < adv; ++i) if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          for (int i = 0; i < p.k_blocks_per_tap; ++i) if (++hb == 2) { hb = 0; hphase ^= 1; }
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        continue;
+      }
       for (int kb = 0; kb < k_blocks; ++kb) {
         if (lane == 0) {
           mbar_wait(&full_bar[stage], phase);
           tcgen05_fence_after();
           const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
-          const uint64_t adesc = make_smem_desc(sa), bdesc = make_smem_desc(sa + a_bytes);
+          const uint64_t adesc = make_smem_desc(sa);
+          const uint64_t bdesc = make_smem_desc(sa + a_bytes + 128u * (uint32_t)p.dbg_bshift) | ((uint64_t)(p.dbg_bbase & 7) << 49);
           if (!(p.dbg_skip_epilogue & 4)) {
 #pragma unroll
             for (int k = 0; k < GEMM_BK / 16; ++k)      // +32 B per K=16 step inside the swizzled row
@@ -488,7 +554,24 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
           const float sc = p.scale[c], sh = p.shift[c];
           const float lo = p.act == ACT_RELU ? 0.f : -INFINITY;
           __half* __restrict__ out = static_cast<__half*>(p.out);
-          if (p.tw == p.Wout && p.tn == 1) {
+          if (p.halo) {
+            // halo mode: accumulator columns y * pitch + x, x < Wout valid; the tile's rows are dealt to the warp groups
+            // (no pooling hook on these layers, so no reduction order to preserve)
+            const int cpr = (p.Wout + 15) >> 4;                                   // 16-column chunks per row
+            for (int ci = grp; ci < p.th * cpr; ci += GEMM_EPI_GROUPS) {
+              const int y = ci / cpr, x0 = (ci - y * cpr) << 4;
+              const int oy = ty * p.th + y;
+              if (oy >= p.Hout) break;
+              __half* op = out + ((size_t)(tg * p.Hout + oy) * p.Wout + x0) * p.M + c;
+              uint32_t v[16];
+              tmem_ld16(taddr + y * p.halo_pitch + x0, v);
+              tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                if (x0 + j < p.Wout) op[(size_t)j * p.M] = __float2half_rn(fmaxf(fmaf(__uint_as_float(v[j]), sc, sh), lo));
+              }
+            }
+          } else if (p.tw == p.Wout && p.tn == 1) {
             // full-width boxes: the tile's valid pixels are consecutive NHWC rows -> linear addressing
             const int y0 = ty * p.th;
             const int valid = min(p.block_n, (p.Hout - y0) * p.Wout);
@@ -917,9 +1000,12 @@ gemm4cta_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
 
 #endif  // B200VQA_GEMM_KERNEL_TU
 
+inline size_t gemm_smem_fixed() { return (2 * GEMM_MAX_STAGES + 8) * 8 + 16 + (size_t)GEMM_EPI_WARPS * 32 * EPI_LD * 4 + 1024; }
 inline size_t gemm_smem_bytes(int block_n, int stages) {
-  return (size_t)stages * (GEMM_BM * GEMM_BK * 2 + (size_t)block_n * GEMM_BK * 2) + (2 * GEMM_MAX_STAGES + 4) * 8 + 16 +
-         (size_t)GEMM_EPI_WARPS * 32 * EPI_LD * 4 + 1024;
+  return (size_t)stages * (GEMM_BM * GEMM_BK * 2 + (size_t)block_n * GEMM_BK * 2) + gemm_smem_fixed();
+}
+inline size_t gemm_smem_bytes_halo(int halo_bytes, int stages) {
+  return (size_t)stages * (GEMM_BM * GEMM_BK * 2) + 2 * (size_t)halo_bytes + gemm_smem_fixed();
 }
 
 // ---------------------------------------------------------------- host: TMA descriptors

@@ -50,10 +50,11 @@ int launch_gemm(const CUtensorMap& map_a, const CUtensorMap& map_b, const GemmPa
   if (p.block_n % 16 || p.block_n < 16 || p.block_n > 256 || p.stages < 2 || p.stages > GEMM_MAX_STAGES) return B200VQA_EINVAL;
   if (p.halo && (p.taps_r != 3 || p.taps_s != 3 || p.conv_stride != 1 || p.conv_pad != 1 || p.idt_blocks || !p.b_is_conv || p.epi != EPI_CONV || p.gap_partial || p.tn != 1 ||
                  p.block_n < p.th * p.halo_pitch || (p.halo_bytes & 1023))) return B200VQA_EINVAL;
-  size_t smem = p.halo ? gemm_smem_bytes_halo(p.halo_bytes, p.stages) : gemm_smem_bytes(p.block_n, p.stages);
+  const bool row_epi = p.epi == EPI_ROW;
+  size_t smem = p.halo ? gemm_smem_bytes_halo(p.halo_bytes, p.stages) : gemm_smem_bytes(p.block_n, p.stages, row_epi);
   if (smem > 227 * 1024) return B200VQA_EINVAL;
   GemmParams q = p;
-  if (const char* e = getenv("B200VQA_GEMM_STAGES")) { int v = atoi(e); if (!p.halo && v >= 2 && v <= GEMM_MAX_STAGES && gemm_smem_bytes(p.block_n, v) <= 227 * 1024) q.stages = v; }
+  if (const char* e = getenv("B200VQA_GEMM_STAGES")) { int v = atoi(e); if (!p.halo && v >= 2 && v <= GEMM_MAX_STAGES && gemm_smem_bytes(p.block_n, v, row_epi) <= 227 * 1024) q.stages = v; }
   if (const char* e = getenv("B200VQA_GEMM_NOEPI")) q.dbg_skip_epilogue = atoi(e);
   if (const char* e = getenv("B200VQA_GEMM_BSHIFT")) q.dbg_bshift = atoi(e);
   if (const char* e = getenv("B200VQA_GEMM_BBASE")) q.dbg_bbase = atoi(e);
@@ -67,7 +68,7 @@ int launch_gemm(const CUtensorMap& map_a, const CUtensorMap& map_b, const GemmPa
     else { VQA_CUDA(cudaEventCreate(&ev.first)); VQA_CUDA(cudaEventCreate(&ev.second)); }
     VQA_CUDA(cudaEventRecord(ev.first, st));
   }
-  smem = q.halo ? gemm_smem_bytes_halo(q.halo_bytes, q.stages) : gemm_smem_bytes(q.block_n, q.stages);
+  smem = q.halo ? gemm_smem_bytes_halo(q.halo_bytes, q.stages) : gemm_smem_bytes(q.block_n, q.stages, row_epi);
   gemm_tcgen05_kernel<<<grid, GEMM_THREADS, smem, st>>>(map_a, map_b, map_eye ? *map_eye : map_a, map_idt ? *map_idt : map_b, q);
   if (prof) {
     VQA_CUDA(cudaEventRecord(ev.second, st));
@@ -172,9 +173,9 @@ int gemm_init_device_attrs() {
   return B200VQA_OK;
 }
 
-int pick_stages(int block_n) {
+int pick_stages(int block_n, bool row_epilogue) {
   const size_t per = GEMM_BM * GEMM_BK * 2 + (size_t)block_n * GEMM_BK * 2;
-  int s = (int)((227 * 1024 - 1024 - 256 - GEMM_EPI_WARPS * 32 * EPI_LD * 4) / per);
+  int s = (int)((227 * 1024 - gemm_smem_fixed(row_epilogue)) / per);
   if (s > 6) s = 6;
   return s;
 }

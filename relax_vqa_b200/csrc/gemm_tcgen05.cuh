@@ -1000,12 +1000,16 @@ gemm4cta_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
 
 #endif  // B200VQA_GEMM_KERNEL_TU
 
-inline size_t gemm_smem_fixed() { return (2 * GEMM_MAX_STAGES + 8) * 8 + 16 + (size_t)GEMM_EPI_WARPS * 32 * EPI_LD * 4 + 1024; }
-inline size_t gemm_smem_bytes(int block_n, int stages) {
-  return (size_t)stages * (GEMM_BM * GEMM_BK * 2 + (size_t)block_n * GEMM_BK * 2) + gemm_smem_fixed();
+// barriers + TMEM slot + alignment slack, plus the row epilogue's transposition tiles (the convolution epilogue stores straight
+// from registers and needs none: its share goes to the operand ring)
+inline size_t gemm_smem_fixed(bool row_epilogue = true) {
+  return (2 * GEMM_MAX_STAGES + 8) * 8 + 16 + (row_epilogue ? (size_t)GEMM_EPI_WARPS * 32 * EPI_LD * 4 : 0) + 1024;
+}
+inline size_t gemm_smem_bytes(int block_n, int stages, bool row_epilogue = true) {
+  return (size_t)stages * (GEMM_BM * GEMM_BK * 2 + (size_t)block_n * GEMM_BK * 2) + gemm_smem_fixed(row_epilogue);
 }
 inline size_t gemm_smem_bytes_halo(int halo_bytes, int stages) {
-  return (size_t)stages * (GEMM_BM * GEMM_BK * 2) + 2 * (size_t)halo_bytes + gemm_smem_fixed();
+  return (size_t)stages * (GEMM_BM * GEMM_BK * 2) + 2 * (size_t)halo_bytes + gemm_smem_fixed(false);
 }
 
 // ---------------------------------------------------------------- host: TMA descriptors
@@ -1021,7 +1025,7 @@ int make_tmap_f16(CUtensorMap* map, const void* base, int rank, const uint64_t* 
 // map_eye / map_idt are only read when p.idt_blocks != 0 (pass nullptr otherwise)
 int launch_gemm(const CUtensorMap& map_a, const CUtensorMap& map_b, const GemmParams& p, int sm_count, cudaStream_t st,
                 const CUtensorMap* map_eye = nullptr, const CUtensorMap* map_idt = nullptr);
-int pick_stages(int block_n);
+int pick_stages(int block_n, bool row_epilogue = true);
 
 // 2-CTA (cta_group::2) linear layer: out[M][N] = act(A[M][K] W[N][K]^T + bias) (+ residual); N % 256 == 0, K % 64 == 0.
 // map_a / map_b must be built with 128-row boxes.

@@ -285,9 +285,9 @@ static int run_conv(b200vqa_ctx* h, const ConvW& cw, const __half* in, int Nimg,
   p.n_tiles = p.tiles_y * cdiv(Nimg, g.tn);
   p.taps_r = stem ? 1 : cw.R; p.taps_s = stem ? 1 : cw.S;
   p.k_blocks_per_tap = stem ? 3 : cw.Cin / GEMM_BK;
-  p.stages = pick_stages(p.block_n);
+  p.stages = pick_stages(p.block_n, false);       // EPI_CONV: no transposition tiles in shared memory
   if (halo) {
-    p.stages = (int)((227 * 1024 - gemm_smem_fixed() - 2 * (size_t)p.halo_bytes) / (GEMM_BM * GEMM_BK * 2));
+    p.stages = (int)((227 * 1024 - gemm_smem_fixed(false) - 2 * (size_t)p.halo_bytes) / (GEMM_BM * GEMM_BK * 2));
     if (p.stages > GEMM_MAX_STAGES) p.stages = GEMM_MAX_STAGES;
   }
   p.b_is_conv = stem ? 0 : 1;

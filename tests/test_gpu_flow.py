@@ -46,10 +46,11 @@ def test_farneback_vs_cv2_and_oracle(ctx, hw):
         assert np.abs(got[0] - orc).max() < 2e-3
 
 
-@pytest.mark.parametrize("impl", [0, 1, 2])
+@pytest.mark.parametrize("impl", [0, 1, 2, 4, 5])
 @pytest.mark.parametrize("hw", [(272, 480), (135, 241), (540, 960), (96, 500)])
 def test_farneback_iteration_variants(ctx, hw, impl):
-    """The three iteration kernels (streaming strips with / without bilinear-tap reuse, 48 x 32 tiles) against cv2,
+    """The iteration kernels (streaming strips with f64 / Kahan sums, 48 x 32 tiles, the software-pipelined variant with the
+    fp32-divide and with the round-1 solve) against cv2,
     on clips with motion and on a static pair whose near-zero flow flips floor() between neighbours (no tap reuse)."""
     from relax_vqa_b200 import ops, synth
     fr, nx = synth.make_clip(5, hw[0], hw[1], 3)
@@ -63,6 +64,8 @@ def test_farneback_iteration_variants(ctx, hw, impl):
     finally:
         ctx.set_flow_impl(0)
     assert np.array_equal(one[0], got[1])                  # batch invariance (segmentation depends on (h, w) only)
+    if impl == 5:                                          # same arithmetic in the same order as the default kernel
+        assert np.array_equal(got, ops.farneback(ctx, _dev(g0), _dev(g1)).cpu().numpy())
     for i in range(3):
         if impl == 2 and i == 2:
             continue      # the tile kernel's uncompensated sliding sums lose ~2e-2 px on near-singular static regions
